@@ -1,0 +1,179 @@
+/*
+ * mvdetr_b200.h -- C ABI of libmvdetr_b200.so: the B200 (sm_100a) implementation of MVDeTr's
+ * per-frame multiview fusion hot path (perspective warp + multi-scale deformable attention).
+ *
+ * Every entry point is what the reference's FFI for this path would bind. "ref:" paths are
+ * relative to the reference tree (hou-yz/MVDeTr @ 66cae15), mvd/ = multiview_detector/.
+ *
+ * Conventions (all functions):
+ *   - plain pointers + sizes, no torch / ATen types;
+ *   - device pointers unless the argument name ends in `_host`;
+ *   - all tensors dense, row-major, layouts given per function;
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream),
+ *     never synchronise, never allocate device memory, re-entrant, no global mutable state
+ *     (exception: the `*_host` convenience entry points, documented below);
+ *   - return 0 (MVD_OK) or a negative MVD_ERR_* for argument errors, or a positive cudaError_t
+ *     if a CUDA runtime call / launch failed. Never throw. `mvd_error_string` decodes both.
+ *     (ref prints launch errors and carries on: mvd/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:948-952;
+ *      ours reports them.)
+ */
+#ifndef MVDETR_B200_H_
+#define MVDETR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MVD_API __attribute__((visibility("default")))
+#else
+#define MVD_API
+#endif
+
+#define MVD_OK 0
+#define MVD_ERR_NULL_POINTER (-1)   /* a required pointer is NULL                                  */
+#define MVD_ERR_BAD_SHAPE (-2)      /* a dimension is <= 0 or the element count overflows int64    */
+#define MVD_ERR_UNSUPPORTED (-3)    /* combination not supported by this entry point               */
+#define MVD_ERR_MISALIGNED (-4)     /* pointer alignment requirement of a fast path not met        */
+#define MVD_ERR_NO_DEVICE (-5)      /* no CUDA device / driver entry point unavailable             */
+
+/* Library version: major*10000 + minor*100 + patch. */
+MVD_API int mvd_version(void);
+
+/* Human-readable text for a return code of any function below (static storage). */
+MVD_API const char* mvd_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention, forward.
+ *   replaces ms_deform_attn_cuda_forward      ref: mvd/models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80
+ *   (kernel ms_deformable_im2col_gpu_kernel   ref: mvd/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299)
+ *   bound by pybind `ms_deform_attn_forward`  ref: mvd/models/ops/src/vision.cpp:13
+ *
+ *   value  [B, S, M, D]          S = sum_l H_l*W_l, level l occupies rows [start[l], start[l]+H_l*W_l)
+ *   shapes [L, 2] int64 (H_l, W_l), start [L] int64        -- device memory, as the reference passes them
+ *   loc    [B, Lq, M, L, P, 2]   (x, y) normalised to [0,1] over each level (outside allowed: zero padding)
+ *   attn   [B, Lq, M, L, P]
+ *   out    [B, Lq, M*D]          fully overwritten (no pre-zeroing needed)
+ *
+ *   out[b,q,m,:] = sum_l sum_p attn[b,q,m,l,p] * bilinear(value_l[b,:,m,:], x*W_l-0.5, y*H_l-0.5)
+ *
+ * The whole batch is processed in one launch; the reference's `im2col_step` batch chunking
+ * (ms_deform_attn_cuda.cu:50-75) does not change results and is validated by the Python mirror.
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_msda_fwd_f32(const float* value, const int64_t* shapes, const int64_t* start,
+                     const float* loc, const float* attn,
+                     int B, int S, int M, int D, int L, int Lq, int P,
+                     float* out, void* stream);
+MVD_API int mvd_msda_fwd_f64(const double* value, const int64_t* shapes, const int64_t* start,
+                     const double* loc, const double* attn,
+                     int B, int S, int M, int D, int L, int Lq, int P,
+                     double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention, backward.
+ *   replaces ms_deform_attn_cuda_backward     ref: mvd/models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153
+ *   (kernels ms_deformable_col2im_gpu_kernel_* ref: mvd/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:301-920)
+ *   bound by pybind `ms_deform_attn_backward` ref: mvd/models/ops/src/vision.cpp:14
+ *
+ *   grad_out   [B, Lq, M*D]
+ *   grad_value [B, S, M, D]        zeroed by this call (cudaMemsetAsync on `stream`), then accumulated
+ *                                  with floating-point atomics => summation order is not deterministic,
+ *                                  exactly as in the reference (cuh:125-152)
+ *   grad_loc   [B, Lq, M, L, P, 2] fully overwritten
+ *   grad_attn  [B, Lq, M, L, P]    fully overwritten
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_msda_bwd_f32(const float* grad_out, const float* value, const int64_t* shapes, const int64_t* start,
+                     const float* loc, const float* attn,
+                     int B, int S, int M, int D, int L, int Lq, int P,
+                     float* grad_value, float* grad_loc, float* grad_attn, void* stream);
+MVD_API int mvd_msda_bwd_f64(const double* grad_out, const double* value, const int64_t* shapes, const int64_t* start,
+                     const double* loc, const double* attn,
+                     int B, int S, int M, int D, int L, int Lq, int P,
+                     double* grad_value, double* grad_loc, double* grad_attn, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Forward for the MVDeTr encoder layout ("view grid"): every level is one camera view of the
+ * same HxW ground-plane grid, S = L*H*W, and the Lq queries are laid out [R, H, W] (R replicas of
+ * the grid, R = L in MVDeTr: mvd/models/trans_world_feat.py:92, mvd/models/mvdetr.py:129-130).
+ * Same maths and same result as mvd_msda_fwd_f32; the grid knowledge (passed from the HOST, so no
+ * device->host read of `shapes` is needed) lets the kernel stage per-(level, head) value windows
+ * in shared memory with TMA. Sampling locations are still arbitrary: samples that fall outside the
+ * staged window take a global-memory path, so the hint can only change speed, never results.
+ *   value [B, L*H*W, M, D], loc [B, R*H*W, M, L, P, 2], attn [B, R*H*W, M, L, P], out [B, R*H*W, M*D]
+ * Returns MVD_ERR_UNSUPPORTED when (D, P, ...) has no tiled instantiation; callers then use
+ * mvd_msda_fwd_f32.
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_msda_fwd_viewgrid_f32(const float* value, const float* loc, const float* attn,
+                              int B, int H, int W, int M, int D, int L, int R, int P,
+                              float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused sampling-location + softmax + deformable attention, forward ("next" row).
+ *   replaces, in one launch, the elementwise tail of MSDeformAttn.forward
+ *       ref: mvd/models/ops/modules/ms_deform_attn.py:100-107   (softmax over L*P; loc = ref + off/(W_l,H_l))
+ *   followed by MSDeformAttnFunction.forward   ref: mvd/models/ops/functions/ms_deform_attn_func.py:22-28
+ *
+ *   value   [B, S, M, D]
+ *   offsets [B, Lq, M, L, P, 2]  raw output of the `sampling_offsets` Linear (pixels of level l)
+ *   logits  [B, Lq, M, L*P]      raw output of the `attention_weights` Linear (pre-softmax)
+ *   ref     [Lr, L, P, 2]        normalised reference points, shared by the batch; query q uses row q % Lr
+ *                                (MVDeTr: Lr = H*W, the table of mvd/models/mvdetr.py:33-71 before its
+ *                                 `.repeat([num_cam,1,1,1])` at :130)
+ *   out     [B, Lq, M*D]
+ *   attn_out (nullable) [B, Lq, M, L, P]  softmax-ed weights, written when non-NULL (needed by backward)
+ *   loc_out  (nullable) [B, Lq, M, L, P, 2] sampling locations, written when non-NULL
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_msda_fused_fwd_f32(const float* value, const int64_t* shapes, const int64_t* start,
+                           const float* offsets, const float* logits, const float* ref,
+                           int B, int S, int M, int D, int L, int Lq, int P, int Lr,
+                           float* out, float* attn_out, float* loc_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Perspective warp (homography + bilinear gather), forward.
+ *   replaces kornia.warp_perspective(src, M, dsize, mode='bilinear', padding_mode='zeros',
+ *                                    align_corners=False)      call site ref: mvd/models/mvdetr.py:194-195
+ *   (kornia is a third-party dependency of the reference, un-vendored and unpinned -- ref: README.md:42;
+ *    the restated algorithm is in DESIGN.md and oracle/warp_ref.c)
+ *
+ *   src [BN, C, Hi, Wi] (NCHW)     Mat [BN, 3, 3] row-major, maps SOURCE pixel (x,y,1) -> DEST pixel
+ *   dst [BN, C, Ho, Wo] (NCHW)     fully overwritten
+ *
+ *   Per view: A = Ndst * Mat * inv(Nsrc), T = inv(A) (normalised coords, computed in-kernel in fp64,
+ *   rounded to fp32), then per dst pixel (u,v): g = (linspace(-1,1,Wo)[u], linspace(-1,1,Ho)[v]),
+ *   (X,Y,Z) = T*(g,1), (x,y) = (X,Y) * (|Z|>1e-8 ? 1/(Z+1e-8) : 1),
+ *   ix = ((x+1)*Wi-1)/2, iy = ((y+1)*Hi-1)/2, 4-tap bilinear with zero padding.
+ *
+ *   `channels_last` != 0 writes dst as [BN, Ho, Wo, C] instead (same values; lets the caller skip a
+ *   permute-copy, ref: mvd/models/trans_world_feat.py:92).
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_warp_fwd_f32(const float* src, const float* Mat,
+                     int BN, int C, int Hi, int Wi, int Ho, int Wo,
+                     float* dst, int channels_last, void* stream);
+
+/* Backward of the warp w.r.t. `src` (the backbone trains through it, ref: mvd/models/mvdetr.py:177-195;
+ * `Mat` carries no gradient in MVDeTr).  Replaces ATen grid_sampler_2d_backward as reached from kornia.
+ *   grad_dst [BN, C, Ho, Wo]   grad_src [BN, C, Hi, Wi] zeroed by this call, then atomically accumulated. */
+MVD_API int mvd_warp_bwd_f32(const float* grad_dst, const float* Mat,
+                     int BN, int C, int Hi, int Wi, int Ho, int Wo,
+                     float* grad_src, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry points (used for end-to-end timing and by non-PyTorch callers):
+ * same arguments, but every pointer is HOST memory (pinned or pageable). They allocate device
+ * scratch, copy in, run the kernel above, copy the result back and synchronise `stream` before
+ * returning. `shapes`/`start` are host int64 arrays here.
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_msda_fwd_f32_host(const float* value_host, const int64_t* shapes_host, const int64_t* start_host,
+                          const float* loc_host, const float* attn_host,
+                          int B, int S, int M, int D, int L, int Lq, int P,
+                          float* out_host, void* stream);
+MVD_API int mvd_warp_fwd_f32_host(const float* src_host, const float* Mat_host,
+                          int BN, int C, int Hi, int Wi, int Ho, int Wo,
+                          float* dst_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVDETR_B200_H_ */

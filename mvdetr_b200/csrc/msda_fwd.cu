@@ -1,0 +1,264 @@
+// Multi-scale deformable attention, forward -- generic kernels (any level shapes, any Lq).
+//
+// Semantics follow the reference kernel ms_deformable_im2col_gpu_kernel
+//   (ref: multiview_detector/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299, bilinear :33-84):
+//   pixel-centre convention h_im = y*H - 0.5, strict (-1, H) validity window, per-corner zero padding,
+//   value laid out [B, S, M, D] so one head-pixel is D contiguous scalars.
+// The design is not the reference's (one thread per output channel, 1024-thread blocks):
+//   * vec4 path (fp32, D = 4..128 power of two): D/4 lanes own one (b,q,m) pair, every corner is ONE
+//     128-bit load per lane, so a D=16 head-pixel (64 B) is fetched by 4 lanes in one request;
+//   * level geometry is converted once per block into shared memory (no int64 loads in the inner loop);
+//   * loc / attn are read through the non-allocating path so L1 is left to the gathered value lines;
+//   * optional FUSED prologue computes loc = ref + off/(W,H) and the softmax over L*P in registers
+//     (ref: multiview_detector/models/ops/modules/ms_deform_attn.py:100-107), see mvd_msda_fused_fwd_f32.
+//   * scalar path (fp32/fp64, any D) for odd head dims and the fp64 gradcheck contract
+//     (ref: multiview_detector/models/ops/test.py:63-86).
+#include "common.cuh"
+
+namespace mvd {
+
+// ---------------------------------------------------------------------------------------------
+// scalar path: one thread per output element
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) msda_fwd_scalar_kernel(
+    const T* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ start,
+    const T* __restrict__ loc, const T* __restrict__ attn, int S, int M, int D, int L, int Lq, int P,
+    int64_t n_out, T* __restrict__ out) {
+  extern __shared__ Level s_lvl[];
+  load_levels(s_lvl, shapes, start, L);
+  __syncthreads();
+
+  const int64_t stride_px = (int64_t)M * D;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_out;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % D);
+    const int64_t pair = idx / D;  // (b*Lq + q)*M + m
+    const int m = (int)(pair % M);
+    const int64_t b = pair / ((int64_t)M * Lq);
+    const T* vb = value + (b * S * M + m) * (int64_t)D + c;
+    const T* lp = loc + pair * L * P * 2;
+    const T* ap = attn + pair * L * P;
+    T acc = 0;
+    for (int l = 0; l < L; ++l) {
+      const Level lv = s_lvl[l];
+      const T* vl = vb + (int64_t)lv.start * stride_px;
+      for (int p = 0; p < P; ++p) {
+        const T x = lp[0], y = lp[1], a = ap[0];
+        lp += 2;
+        ap += 1;
+        const T h_im = y * lv.H - (T)0.5;
+        const T w_im = x * lv.W - (T)0.5;
+        if (h_im > (T)-1 && w_im > (T)-1 && h_im < (T)lv.H && w_im < (T)lv.W) {
+          const int h0 = (int)floor(h_im), w0 = (int)floor(w_im);
+          const T lh = h_im - h0, lw = w_im - w0, hh = 1 - lh, hw = 1 - lw;
+          const bool top = h0 >= 0, bot = h0 + 1 <= lv.H - 1, lef = w0 >= 0, rig = w0 + 1 <= lv.W - 1;
+          const T* p00 = vl + ((int64_t)h0 * lv.W + w0) * stride_px;
+          const T v1 = (top && lef) ? p00[0] : (T)0;
+          const T v2 = (top && rig) ? p00[stride_px] : (T)0;
+          const T v3 = (bot && lef) ? p00[(int64_t)lv.W * stride_px] : (T)0;
+          const T v4 = (bot && rig) ? p00[(int64_t)(lv.W + 1) * stride_px] : (T)0;
+          const T val = hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4;
+          acc += val * a;
+        }
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vec4 path: D/4 lanes per (b,q,m) pair, 128-bit corner loads
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int D, bool FUSED>
+__global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
+    const float* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ start,
+    const float* __restrict__ loc_or_off, const float* __restrict__ attn_or_logit, const float* __restrict__ ref,
+    int S, int M, int L, int Lq, int P, int Lr, int64_t n_pairs, float* __restrict__ out,
+    float* __restrict__ attn_out, float* __restrict__ loc_out) {
+  constexpr int G = D / 4;  // lanes per pair
+  constexpr int PAIRS = 256 / G;
+  extern __shared__ Level s_lvl[];
+  load_levels(s_lvl, shapes, start, L);
+  __syncthreads();
+
+  const int sub = threadIdx.x % G;
+  const int64_t pair_raw = (int64_t)blockIdx.x * PAIRS + threadIdx.x / G;
+  const bool valid = pair_raw < n_pairs;  // tail lanes recompute the last pair (keeps shuffles full-warp)
+  const int64_t pair = valid ? pair_raw : n_pairs - 1;
+  const int m = (int)(pair % M);
+  const int64_t bq = pair / M;
+  const int64_t b = bq / Lq;
+  const int q = (int)(bq % Lq);
+  const int LP = L * P;
+  const int64_t stride_px = (int64_t)M * D;
+  const float* vb = value + (b * S * M + m) * (int64_t)D + sub * 4;
+  const float* lp = loc_or_off + pair * LP * 2;
+  const float* ap = attn_or_logit + pair * LP;
+
+  // FUSED: softmax statistics over the L*P logits of this pair (lanes of the group split the logits).
+  float smax = 0.f, ssum = 1.f;
+  const float* rp = nullptr;
+  if (FUSED) {
+    float mx = -INFINITY;
+    for (int i = sub; i < LP; i += G) mx = fmaxf(mx, ld_stream(ap + i));
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, G));
+    float sum = 0.f;
+    for (int i = sub; i < LP; i += G) sum += expf(__ldg(ap + i) - mx);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, G);
+    smax = mx;
+    ssum = sum;
+    rp = ref + (int64_t)(q % Lr) * LP * 2;
+  }
+
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const Level lv = s_lvl[l];
+    const float* vl = vb + (int64_t)lv.start * stride_px;
+    const float fH = (float)lv.H, fW = (float)lv.W;
+#pragma unroll 2
+    for (int p = 0; p < P; ++p) {
+      float2 xy;
+      float a;
+      if (FUSED) {
+        const float2 off = __ldg(reinterpret_cast<const float2*>(lp));
+        const float2 r = __ldg(reinterpret_cast<const float2*>(rp));
+        xy.x = r.x + off.x / fW;
+        xy.y = r.y + off.y / fH;
+        a = expf(__ldg(ap) - smax) / ssum;
+        rp += 2;
+        if (sub == 0 && valid) {
+          if (attn_out) attn_out[pair * LP + l * P + p] = a;
+          if (loc_out) reinterpret_cast<float2*>(loc_out)[pair * LP + l * P + p] = xy;
+        }
+      } else {
+        xy = __ldg(reinterpret_cast<const float2*>(lp));
+        a = __ldg(ap);
+      }
+      lp += 2;
+      ap += 1;
+      // product rounded before the subtraction, as the reference's float*int - 0.5 (double) does (cuh:285-286)
+      const float h_im = __fsub_rn(__fmul_rn(xy.y, fH), 0.5f);
+      const float w_im = __fsub_rn(__fmul_rn(xy.x, fW), 0.5f);
+      if (h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW) {
+        const float hf = floorf(h_im), wf = floorf(w_im);
+        const int h0 = (int)hf, w0 = (int)wf;
+        const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+        const bool top = h0 >= 0, bot = h0 + 1 <= lv.H - 1, lef = w0 >= 0, rig = w0 + 1 <= lv.W - 1;
+        const float* p00 = vl + ((int64_t)h0 * lv.W + w0) * stride_px;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v1 = (top && lef) ? ldg4(p00) : z;
+        const float4 v2 = (top && rig) ? ldg4(p00 + stride_px) : z;
+        const float4 v3 = (bot && lef) ? ldg4(p00 + (int64_t)lv.W * stride_px) : z;
+        const float4 v4 = (bot && rig) ? ldg4(p00 + (int64_t)(lv.W + 1) * stride_px) : z;
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        acc.x += (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x) * a;
+        acc.y += (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y) * a;
+        acc.z += (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z) * a;
+        acc.w += (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w) * a;
+      }
+    }
+  }
+  if (valid) *reinterpret_cast<float4*>(out + pair * D + sub * 4) = acc;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+template <typename T>
+static int launch_scalar(const T* value, const int64_t* shapes, const int64_t* start, const T* loc, const T* attn,
+                         int B, int S, int M, int D, int L, int Lq, int P, T* out, cudaStream_t st) {
+  const int64_t n_out = (int64_t)B * Lq * M * D;
+  const int64_t blocks64 = ceil_div64(n_out, 256);
+  const int blocks = (int)(blocks64 > (int64_t)kNumSMs * 64 ? (int64_t)kNumSMs * 64 : blocks64);
+  msda_fwd_scalar_kernel<T><<<blocks, 256, L * sizeof(Level), st>>>(value, shapes, start, loc, attn, S, M, D, L, Lq,
+                                                                    P, n_out, out);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
+
+template <int D, bool FUSED>
+static int launch_vec4(const float* value, const int64_t* shapes, const int64_t* start, const float* loc,
+                       const float* attn, const float* ref, int B, int S, int M, int L, int Lq, int P, int Lr,
+                       float* out, float* attn_out, float* loc_out, cudaStream_t st) {
+  constexpr int PAIRS = 256 / (D / 4);
+  const int64_t n_pairs = (int64_t)B * Lq * M;
+  const int64_t blocks = ceil_div64(n_pairs, PAIRS);
+  if (blocks > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
+  msda_fwd_vec4_kernel<D, FUSED><<<(int)blocks, 256, L * sizeof(Level), st>>>(
+      value, shapes, start, loc, attn, ref, S, M, L, Lq, P, Lr, n_pairs, out, attn_out, loc_out);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
+
+template <bool FUSED>
+static int dispatch_vec4(const float* value, const int64_t* shapes, const int64_t* start, const float* loc,
+                         const float* attn, const float* ref, int B, int S, int M, int D, int L, int Lq, int P,
+                         int Lr, float* out, float* attn_out, float* loc_out, cudaStream_t st) {
+#define MVD_CASE(DD)                                                                                              \
+  case DD:                                                                                                        \
+    return launch_vec4<DD, FUSED>(value, shapes, start, loc, attn, ref, B, S, M, L, Lq, P, Lr, out, attn_out,     \
+                                  loc_out, st)
+  switch (D) {
+    MVD_CASE(4);
+    MVD_CASE(8);
+    MVD_CASE(16);
+    MVD_CASE(32);
+    MVD_CASE(64);
+    MVD_CASE(128);
+    default:
+      return MVD_ERR_UNSUPPORTED;
+  }
+#undef MVD_CASE
+}
+
+static bool vec4_ok(int D) { return D == 4 || D == 8 || D == 16 || D == 32 || D == 64 || D == 128; }
+
+static int check_dims(int B, int S, int M, int D, int L, int Lq, int P) {
+  if (B <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq <= 0 || P <= 0) return MVD_ERR_BAD_SHAPE;
+  if (L > 4096) return MVD_ERR_BAD_SHAPE;  // level table lives in shared memory
+  return MVD_OK;
+}
+
+}  // namespace mvd
+
+using namespace mvd;
+
+extern "C" int mvd_msda_fwd_f32(const float* value, const int64_t* shapes, const int64_t* start, const float* loc,
+                                const float* attn, int B, int S, int M, int D, int L, int Lq, int P, float* out,
+                                void* stream) {
+  if (!value || !shapes || !start || !loc || !attn || !out) return MVD_ERR_NULL_POINTER;
+  if (int e = check_dims(B, S, M, D, L, Lq, P)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec4_ok(D) && aligned16(value) && aligned16(out) && aligned8(loc))
+    return dispatch_vec4<false>(value, shapes, start, loc, attn, nullptr, B, S, M, D, L, Lq, P, 1, out, nullptr,
+                                nullptr, st);
+  return launch_scalar<float>(value, shapes, start, loc, attn, B, S, M, D, L, Lq, P, out, st);
+}
+
+extern "C" int mvd_msda_fwd_f64(const double* value, const int64_t* shapes, const int64_t* start,
+                                const double* loc, const double* attn, int B, int S, int M, int D, int L, int Lq,
+                                int P, double* out, void* stream) {
+  if (!value || !shapes || !start || !loc || !attn || !out) return MVD_ERR_NULL_POINTER;
+  if (int e = check_dims(B, S, M, D, L, Lq, P)) return e;
+  return launch_scalar<double>(value, shapes, start, loc, attn, B, S, M, D, L, Lq, P, out, (cudaStream_t)stream);
+}
+
+extern "C" int mvd_msda_fused_fwd_f32(const float* value, const int64_t* shapes, const int64_t* start,
+                                      const float* offsets, const float* logits, const float* ref, int B, int S,
+                                      int M, int D, int L, int Lq, int P, int Lr, float* out, float* attn_out,
+                                      float* loc_out, void* stream) {
+  if (!value || !shapes || !start || !offsets || !logits || !ref || !out) return MVD_ERR_NULL_POINTER;
+  if (int e = check_dims(B, S, M, D, L, Lq, P)) return e;
+  if (Lr <= 0) return MVD_ERR_BAD_SHAPE;
+  if (!vec4_ok(D)) return MVD_ERR_UNSUPPORTED;
+  if (!aligned16(value) || !aligned16(out) || !aligned8(offsets) || !aligned8(ref) ||
+      (loc_out && !aligned8(loc_out)))
+    return MVD_ERR_MISALIGNED;
+  return dispatch_vec4<true>(value, shapes, start, offsets, logits, ref, B, S, M, D, L, Lq, P, Lr, out, attn_out,
+                             loc_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C ABI.
+
+  ms_deform_attn_forward / ms_deform_attn_backward
+        same names, argument order and error behaviour as the pybind module `MultiScaleDeformableAttention`
+        (ref: multiview_detector/models/ops/src/vision.cpp:13-15, ms_deform_attn.h:20-61,
+         cuda/ms_deform_attn_cuda.cu:20-153)
+  MSDeformAttnFunction
+        same autograd.Function as ref: multiview_detector/models/ops/functions/ms_deform_attn_func.py:21-38
+  msda_fused_forward
+        extra entry point: loc/softmax arithmetic of ms_deform_attn.py:100-107 inside the kernel
+  warp_perspective
+        kornia.warp_perspective signature as used at ref: multiview_detector/models/mvdetr.py:194-195
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libmvdetr_b200.so.
+"""
+import os
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _C
+
+_VIEWGRID = os.environ.get("MVDETR_B200_VIEWGRID", "1") != "0"
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _on_device:
+    """Cheap device guard: only switches when the tensor lives on a non-current device."""
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
+                       grad_output=None):
+    """The reference's preconditions, same order and wording (ms_deform_attn.h:29-38, ms_deform_attn_cuda.cu:28-52)."""
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)]
+    if grad_output is not None:
+        named.append(("grad_output", grad_output))
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+    for name, t in named:
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")
+    if value.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError(f'"ms_deform_attn_forward_cuda" not implemented for \'{value.dtype}\'')
+    for name, t in named[3:]:
+        if t.dtype != value.dtype:
+            raise RuntimeError(f"{name} must have the dtype of value ({value.dtype}), got {t.dtype}")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64 tensors")
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
+        raise RuntimeError("expected value [B,S,M,D], sampling_loc [B,Lq,M,L,P,2], attn_weight [B,Lq,M,L,P]")
+    B, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    if tuple(sampling_loc.shape) != (B, Lq, M, L, P, 2) or tuple(attn_weight.shape) != (B, Lq, M, L, P):
+        raise RuntimeError(f"inconsistent shapes: value {tuple(value.shape)}, sampling_loc "
+                           f"{tuple(sampling_loc.shape)}, attn_weight {tuple(attn_weight.shape)}, levels {L}")
+    if level_start_index.numel() != L:
+        raise RuntimeError("level_start_index must have one entry per level")
+    step = min(B, int(im2col_step))
+    if step <= 0 or B % step != 0:
+        raise RuntimeError(f"batch({B}) must divide im2col_step({step})")
+    if grad_output is not None and grad_output.numel() != B * Lq * M * D:
+        raise RuntimeError("grad_output must have B*Lq*M*D elements")
+    return B, S, M, D, L, Lq, P
+
+
+def _viewgrid_geometry(value, spatial_shapes, S, L, Lq):
+    """Returns (H, W, R) when every level is the same HxW grid and the queries are R copies of that grid
+    (MVDeTr's encoder layout), else None. Reads `spatial_shapes` back to the host (one small sync; the reference's
+    own caller already synchronises on the same tensor at ms_deform_attn.py:94)."""
+    if not _VIEWGRID or value.dtype != torch.float32 or S % L != 0:
+        return None
+    hw = S // L
+    if Lq % hw != 0:
+        return None
+    shapes = spatial_shapes.tolist()
+    H, W = shapes[0]
+    if H * W != hw or any(s != [H, W] for s in shapes):
+        return None
+    return H, W, Lq // hw
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    """-> output [B, Lq, M*D]. Drop-in for MSDA.ms_deform_attn_forward (ms_deform_attn_func.py:25)."""
+    B, S, M, D, L, Lq, P = _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                              im2col_step)
+    out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    with _on_device(value):
+        if value.dtype == torch.float32:
+            geo = _viewgrid_geometry(value, spatial_shapes, S, L, Lq)
+            if geo is not None:
+                H, W, R = geo
+                rc = _C.lib.mvd_msda_fwd_viewgrid_f32(value.data_ptr(), sampling_loc.data_ptr(),
+                                                      attn_weight.data_ptr(), B, H, W, M, D, L, R, P,
+                                                      out.data_ptr(), _stream(value))
+                if rc == 0:
+                    return out
+                if rc != -3:  # MVD_ERR_UNSUPPORTED -> generic kernel
+                    _C.check(rc, "mvd_msda_fwd_viewgrid_f32")
+            fn = _C.lib.mvd_msda_fwd_f32
+        else:
+            fn = _C.lib.mvd_msda_fwd_f64
+        rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                attn_weight.data_ptr(), B, S, M, D, L, Lq, P, out.data_ptr(), _stream(value))
+    _C.check(rc, "mvd_msda_fwd")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight]. Drop-in for MSDA.ms_deform_attn_backward."""
+    B, S, M, D, L, Lq, P = _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                              im2col_step, grad_output)
+    grad_value = torch.empty_like(value)  # zeroed inside the C call
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    fn = _C.lib.mvd_msda_bwd_f32 if value.dtype == torch.float32 else _C.lib.mvd_msda_bwd_f64
+    with _on_device(value):
+        rc = fn(grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                sampling_loc.data_ptr(), attn_weight.data_ptr(), B, S, M, D, L, Lq, P, grad_value.data_ptr(),
+                grad_loc.data_ptr(), grad_attn.data_ptr(), _stream(value))
+    _C.check(rc, "mvd_msda_bwd")
+    return [grad_value, grad_loc, grad_attn]
+
+
+class MSDeformAttnFunction(Function):
+    """Same contract as ref ms_deform_attn_func.py:21-38: apply(value, value_spatial_shapes,
+    value_level_start_index, sampling_locations, attention_weights, im2col_step)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                        attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, start, loc, attn = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = ms_deform_attn_backward(value, shapes, start, loc, attn,
+                                                                  grad_output.contiguous(), ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None
+
+
+def msda_viewgrid_forward(value, sampling_loc, attn_weight, H, W):
+    """Forward for the MVDeTr encoder layout with the grid given as host ints (no device->host read):
+    value [B, L*H*W, M, D], sampling_loc [B, R*H*W, M, L, P, 2], attn_weight [B, R*H*W, M, L, P]."""
+    B, S, M, D = value.shape
+    Lq, L, P = sampling_loc.shape[1], sampling_loc.shape[3], sampling_loc.shape[4]
+    if S != L * H * W or Lq % (H * W) != 0:
+        raise RuntimeError("msda_viewgrid_forward: value/queries are not L resp. R copies of an HxW grid")
+    for name, t in (("value", value), ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor")
+    out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    with _on_device(value):
+        rc = _C.lib.mvd_msda_fwd_viewgrid_f32(value.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(), B, H,
+                                              W, M, D, L, Lq // (H * W), P, out.data_ptr(), _stream(value))
+    _C.check(rc, "mvd_msda_fwd_viewgrid_f32")
+    return out
+
+
+def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits, ref_table, want_aux=False):
+    """out = MSDA(value, loc = ref + offsets/(W_l,H_l), attn = softmax(logits)) in one kernel (inference path).
+
+    value [B,S,M,D] fp32; offsets [B,Lq,M,L,P,2] and logits [B,Lq,M,L*P]: raw Linear outputs; ref_table [Lr,L,P,2]
+    (query q reads row q % Lr). Returns out [B,Lq,M*D], plus (attn, loc) when want_aux."""
+    B, S, M, D = value.shape
+    _, Lq, _, L, P, _ = offsets.shape
+    for name, t in (("value", value), ("offsets", offsets), ("logits", logits), ("ref_table", ref_table)):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor")
+    if logits.numel() != B * Lq * M * L * P or tuple(ref_table.shape[1:]) != (L, P, 2):
+        raise RuntimeError("msda_fused_forward: inconsistent shapes")
+    out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    attn = torch.empty((B, Lq, M, L, P), dtype=value.dtype, device=value.device) if want_aux else None
+    loc = torch.empty_like(offsets) if want_aux else None
+    with _on_device(value):
+        rc = _C.lib.mvd_msda_fused_fwd_f32(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                           offsets.data_ptr(), logits.data_ptr(), ref_table.data_ptr(), B, S, M, D, L,
+                                           Lq, P, ref_table.shape[0], out.data_ptr(),
+                                           attn.data_ptr() if want_aux else None,
+                                           loc.data_ptr() if want_aux else None, _stream(value))
+    _C.check(rc, "mvd_msda_fused_fwd_f32")
+    return (out, attn, loc) if want_aux else out
+
+
+class _WarpPerspective(Function):
+    @staticmethod
+    def forward(ctx, src, mat, Ho, Wo, channels_last):
+        BN, C, Hi, Wi = src.shape
+        shape = (BN, Ho, Wo, C) if channels_last else (BN, C, Ho, Wo)
+        dst = torch.empty(shape, dtype=src.dtype, device=src.device)
+        with _on_device(src):
+            rc = _C.lib.mvd_warp_fwd_f32(src.data_ptr(), mat.data_ptr(), BN, C, Hi, Wi, Ho, Wo, dst.data_ptr(),
+                                         1 if channels_last else 0, _stream(src))
+        _C.check(rc, "mvd_warp_fwd_f32")
+        ctx.save_for_backward(mat)
+        ctx.geom = (BN, C, Hi, Wi, Ho, Wo, channels_last)
+        return dst
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_dst):
+        (mat,) = ctx.saved_tensors
+        BN, C, Hi, Wi, Ho, Wo, channels_last = ctx.geom
+        if channels_last:
+            grad_dst = grad_dst.permute(0, 3, 1, 2)
+        grad_dst = grad_dst.contiguous()
+        grad_src = torch.empty((BN, C, Hi, Wi), dtype=grad_dst.dtype, device=grad_dst.device)
+        with _on_device(grad_dst):
+            rc = _C.lib.mvd_warp_bwd_f32(grad_dst.data_ptr(), mat.data_ptr(), BN, C, Hi, Wi, Ho, Wo,
+                                         grad_src.data_ptr(), _stream(grad_dst))
+        _C.check(rc, "mvd_warp_bwd_f32")
+        return grad_src, None, None, None, None
+
+
+def warp_perspective(src, M, dsize, mode="bilinear", padding_mode="zeros", align_corners=None, channels_last=False):
+    """kornia.warp_perspective(src [BN,C,H,W], M [BN,3,3] (src pixel -> dst pixel), dsize=(Ho,Wo)) -> [BN,C,Ho,Wo].
+
+    Only the combination MVDeTr's hot path uses is implemented in CUDA (mvdetr.py:194-195):
+    mode='bilinear', padding_mode='zeros', align_corners=False; anything else raises NotImplementedError.
+    Differentiable w.r.t. `src`. `channels_last=True` (extension) returns [BN,Ho,Wo,C]."""
+    if mode != "bilinear" or padding_mode != "zeros" or align_corners is not False:
+        raise NotImplementedError(
+            "mvdetr_b200.warp_perspective implements mode='bilinear', padding_mode='zeros', align_corners=False "
+            f"(got mode={mode!r}, padding_mode={padding_mode!r}, align_corners={align_corners!r})")
+    if not torch.is_tensor(src) or not torch.is_tensor(M):
+        raise TypeError("Input type is not a torch.Tensor")
+    if src.dim() != 4:
+        raise ValueError(f"Input src must be a BxCxHxW tensor. Got {tuple(src.shape)}")
+    if M.dim() != 3 or tuple(M.shape[-2:]) != (3, 3) or M.shape[0] != src.shape[0]:
+        raise ValueError(f"Input M must be a Bx3x3 tensor. Got {tuple(M.shape)}")
+    if not src.is_cuda:
+        raise RuntimeError("mvdetr_b200.warp_perspective: src must be a CUDA tensor (no CPU fallback)")
+    if src.dtype != torch.float32:
+        raise RuntimeError(f"mvdetr_b200.warp_perspective: fp32 only, got {src.dtype}")
+    Ho, Wo = int(dsize[0]), int(dsize[1])
+    mat = M.detach().to(device=src.device, dtype=torch.float32).contiguous()
+    return _WarpPerspective.apply(src.contiguous(), mat, Ho, Wo, bool(channels_last))
