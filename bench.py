@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- multiview fusion frames/s on synthetic Wildtrack-shaped input (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA kernels behind the C ABI)
+  python bench.py --impl reference [...]                          the reference's CPU-capable path (oracle port)
+  torchrun --nproc-per-node N ... bench.py --gpus N ...           N>1: camera views sharded across ranks
+
+One step = one frame through the fusion stage of MVDeTr.forward: perspective warp of the 7 per-view feature maps
+[7,128,90,160] -> [7,128,120,360] followed by DeformTransWorldFeat (3 deformable-attention encoder layers), i.e.
+ref multiview_detector/models/mvdetr.py:194-202. The backbone is out of scope; features are synthetic.
+Prints ONE JSON line (see the keys below); everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOAD = "wildtrack_7view_1080p_resnet18feat_deform_trans"
+HIDDEN, HEADS, POINTS, LAYERS = 128, 8, 4, 3
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy kernel)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def msda_algorithmic_bytes(B, S, M, D, L, Lq, P, fused_ref_rows=0):
+    """value + loc/offsets + attn/logits + out, fp32 (+ the compact reference table when fused)."""
+    n = B * S * M * D + B * Lq * M * L * P * 2 + B * Lq * M * L * P + B * Lq * M * D + fused_ref_rows * L * P * 2
+    return 4 * n
+
+
+def warp_algorithmic_bytes(BN, C, Hi, Wi, Ho, Wo):
+    return 4 * BN * C * (Hi * Wi + Ho * Wo) + 36 * BN
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_fusion(device, seed=0):
+    """Random-init fusion stage with Wildtrack geometry; offsets/attention made query dependent (SURVEY 8d config 2:
+    default init has zero weight => every query samples the same fixed ring, an unrealistically cache-friendly
+    pattern)."""
+    from mvdetr_b200 import synthetic
+    from mvdetr_b200.fusion import MultiviewFusion
+    torch.manual_seed(seed)
+    ds = synthetic.wildtrack_like(seed=seed)
+    fusion = MultiviewFusion(ds, base_dim=HIDDEN, hidden_dim=HIDDEN, nhead=HEADS, n_points=POINTS)
+    with torch.no_grad():
+        for layer in fusion.world_feat.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    return ds, fusion.to(device).eval()
+
+
+def synthetic_frames(ds, n, seed=0, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    feats, Ms = [], []
+    for _ in range(n):
+        f = torch.randn(ds.num_cam, HIDDEN, *ds.Rimg_shape, generator=g)
+        feats.append(f.pin_memory() if pin else f)
+        Ms.append(torch.eye(3).view(1, 1, 3, 3).repeat(1, ds.num_cam, 1, 1))
+    return feats, Ms
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU-capable path restated in oracle/torch_port.py (kind "port")
+# ------------------------------------------------------------------------------------------------------------
+def cpu_strip_problem(seed=0, strip=4):
+    """Bounded sample of the workload: all 7 views, but a 1/strip-wide strip of the ground grid (120 x 360/strip).
+    Every stage of the path is linear in the number of ground cells, so frames/s = (1/strip) / seconds."""
+    from mvdetr_b200 import synthetic
+    from mvdetr_b200.projection import create_reference_map, frame_projection_mats, world_grid_projection_mats
+    from mvdetr_b200.world_feat import DeformTransWorldFeat
+    torch.manual_seed(seed)
+    ds = synthetic.wildtrack_like(seed=seed)
+    ds.Rworld_shape = [ds.Rworld_shape[0], ds.Rworld_shape[1] // strip]
+    ref = create_reference_map(ds, POINTS).repeat([ds.num_cam, 1, 1, 1])
+    model = DeformTransWorldFeat(ds.num_cam, ds.Rworld_shape, HIDDEN, hidden_dim=HIDDEN, nhead=HEADS,
+                                 n_points=POINTS, reference_points=ref).eval()
+    with torch.no_grad():
+        for layer in model.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    proj = frame_projection_mats(world_grid_projection_mats(ds), torch.eye(3).view(1, 1, 3, 3).repeat(1, 7, 1, 1),
+                                 ds.img_reduce)
+    feats, _ = synthetic_frames(ds, 1, seed)
+    return ds, sd, ref, proj, feats[0]
+
+
+def cpu_step(ds, sd, ref, proj, feat):
+    from oracle import torch_port as tp
+    with torch.no_grad():
+        world = tp.warp_perspective(feat, proj, tuple(ds.Rworld_shape))
+        return tp.world_feat_forward(sd, world.view(1, ds.num_cam, HIDDEN, *ds.Rworld_shape), ref, n_heads=HEADS,
+                                     n_points=POINTS, n_layers=LAYERS)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    strip = 4
+    prob = cpu_strip_problem(strip=strip)
+    cores = torch.get_num_threads()
+    for _ in range(max(1, args.warmup)):
+        cpu_step(*prob)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(*prob)
+    dt = (time.perf_counter() - t0) / args.steps
+    fps = (1.0 / strip) / dt
+    sample = f"all 7 views, 120x{360 // strip} strip (1/{strip}) of the 120x360 ground grid per step; fp32 torch CPU"
+    line = {"impl": "reference", "metric": "multiview_frames_per_sec", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "views": 7, "feat": [7, HIDDEN, 90, 160], "world_grid": [120, 360],
+                       "layers": LAYERS, "heads": HEADS, "points": POINTS},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(reps=3, strip=4):
+    prob = cpu_strip_problem(strip=strip)
+    cpu_step(*prob)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_step(*prob)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": (1.0 / strip) / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{reps} reps of all 7 views on a 120x{360 // strip} strip (1/{strip}) of the ground grid",
+            "host_cpus": os.cpu_count(), "seconds_per_frame_equiv": dt * strip}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def time_kernel_events(fn, iters, flush=None):
+    """Average device time of fn() in microseconds, CUDA events on the current stream, optional L2 flush between."""
+    evs = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) * 1e3 for a, b in evs]
+    return sum(ts) / len(ts), min(ts)
+
+
+def kernel_breakdown(fusion, ds, device, iters=20):
+    """Per-kernel device times for the two hot-path kernels on this workload's real tensors (L2 flushed between
+    launches with a 512 MB memset), plus the reference's own CUDA op on the same inputs when oracle/_ref exists."""
+    from mvdetr_b200 import ops
+    wf = fusion.world_feat
+    N, (Hg, Wg) = ds.num_cam, ds.Rworld_shape
+    Hd, Wd = Hg // 2, Wg // 2
+    Lq = S = N * Hd * Wd
+    D = HIDDEN // HEADS
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    feat = torch.randn(N, HIDDEN, *ds.Rimg_shape, generator=g).to(device)
+    proj = fusion.projection(torch.eye(3).view(1, 1, 3, 3).repeat(1, N, 1, 1)).to(device)
+    res = {}
+    with torch.no_grad():
+        t, tmin = time_kernel_events(lambda: ops.warp_perspective(feat, proj, (Hg, Wg), align_corners=False,
+                                                                  channels_last=True), iters, flush)
+        wb = warp_algorithmic_bytes(N, HIDDEN, *ds.Rimg_shape, Hg, Wg)
+        res["warp"] = {"us": t, "us_min": tmin, "bytes": wb, "GBps": wb / t / 1e3}
+        # realistic MSDA inputs: run the model's own first layer projections on a real frame
+        world = ops.warp_perspective(feat, proj, (Hg, Wg), align_corners=False).view(1, N, HIDDEN, Hg, Wg)
+        x = wf.downsample(world.view(N, HIDDEN, Hg, Wg))
+        src = x.view(1, N, HIDDEN, Hd, Wd).permute(0, 1, 3, 4, 2).reshape(1, S, HIDDEN)
+        pos = (wf.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) + wf.lvl_embedding.view(1, N, 1, HIDDEN)
+               ).view(1, S, HIDDEN)
+        attn_mod = wf.encoder.layers[0].self_attn
+        value = attn_mod.value_proj(src).view(1, S, HEADS, D).contiguous()
+        offsets = attn_mod.sampling_offsets(src + pos).view(1, Lq, HEADS, N, POINTS, 2).contiguous()
+        logits = attn_mod.attention_weights(src + pos).view(1, Lq, HEADS, N * POINTS).contiguous()
+        geo = wf._level_geometry(N, Hd, Wd, torch.device(device))
+        table = wf.encoder.ref_table
+        out, attn, loc = ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table, want_aux=True)
+        t, tmin = time_kernel_events(lambda: ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits,
+                                                                    table), iters, flush)
+        fb = msda_algorithmic_bytes(1, S, HEADS, D, N, Lq, POINTS, fused_ref_rows=table.shape[0])
+        res["msda_fused_fwd"] = {"us": t, "us_min": tmin, "bytes": fb, "GBps": fb / t / 1e3}
+        t, tmin = time_kernel_events(lambda: ops.ms_deform_attn_forward(value, geo.shapes, geo.start, loc, attn, 64),
+                                     iters, flush)
+        ub = msda_algorithmic_bytes(1, S, HEADS, D, N, Lq, POINTS)
+        res["msda_fwd"] = {"us": t, "us_min": tmin, "bytes": ub, "GBps": ub / t / 1e3}
+        go = torch.randn_like(out)
+        t, tmin = time_kernel_events(lambda: ops.ms_deform_attn_backward(value, geo.shapes, geo.start, loc, attn, go,
+                                                                         64), max(5, iters // 2), flush)
+        bb = 4 * (3 * S * HEADS * D + Lq * HEADS * D + 2 * 3 * Lq * HEADS * N * POINTS)
+        res["msda_bwd"] = {"us": t, "us_min": tmin, "bytes": bb, "GBps": bb / t / 1e3}
+        ref_so = os.path.join(REPO, "oracle", "_ref", "MultiScaleDeformableAttention.so")
+        if os.path.exists(ref_so):
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttention", ref_so)
+                ext = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(ext)
+                t, tmin = time_kernel_events(lambda: ext.ms_deform_attn_forward(value, geo.shapes, geo.start, loc,
+                                                                                attn, 64), iters, flush)
+                res["ref_cuda_msda_fwd"] = {"us": t, "us_min": tmin, "GBps": ub / t / 1e3}
+                t, tmin = time_kernel_events(lambda: ext.ms_deform_attn_backward(value, geo.shapes, geo.start, loc,
+                                                                                 attn, go, 64), max(5, iters // 2),
+                                             flush)
+                res["ref_cuda_msda_bwd"] = {"us": t, "us_min": tmin, "GBps": bb / t / 1e3}
+                diff = (ext.ms_deform_attn_forward(value, geo.shapes, geo.start, loc, attn, 64) - out).abs().max()
+                res["ref_cuda_max_abs_diff"] = diff.item()
+            except Exception as e:  # comparator only; never fatal
+                res["ref_cuda_error"] = repr(e)[:200]
+    del flush
+    return res
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    torch.backends.cuda.matmul.allow_tf32 = False  # dense glue stays full fp32, like the reference
+    torch.backends.cudnn.allow_tf32 = False
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from mvdetr_b200.fusion import FrameRunner
+    ds, fusion = build_fusion(device)
+    BN = ds.num_cam
+    feat_shape = (BN, HIDDEN, *ds.Rimg_shape)
+    if world > 1:
+        from mvdetr_b200.sharded import ShardedFrameRunner
+        runner = ShardedFrameRunner(fusion, feat_shape, device, rank, world)
+        mode = runner.mode
+    else:
+        runner = FrameRunner(fusion, feat_shape, device, use_graph=True, depth=2)
+        mode = "single"
+
+    n_frames = 4  # distinct synthetic frames cycled through (4 x 51.6 MB of features > L2)
+    feats_pinned, Ms = synthetic_frames(ds, n_frames, seed=0, pin=True)
+    feats_dev = [f.to(device) for f in feats_pinned]
+    projs_dev = [fusion.projection(M).to(device) for M in Ms]
+    out_shape = (1, HIDDEN, *ds.Rworld_shape)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`): inputs already in HBM, alternate the two slots ----
+    for s in range(runner.depth):
+        runner.load(feats_dev[s % n_frames], projs_dev[s % n_frames], slot=s)
+    for i in range(args.warmup):
+        runner.step(i % runner.depth)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(runner.compute):
+        e0.record()
+    for i in range(args.steps):
+        runner.step(i % runner.depth)
+    with torch.cuda.stream(runner.compute):
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    frames_per_step = runner.frames_per_step if world > 1 else 1
+    value = frames_per_step * 1e3 / ms_per_step
+
+    # ---- end to end: pinned host features in, fused world feature out, every step ----
+    outs_pinned = [torch.empty(out_shape).pin_memory() for _ in range(n_frames)]
+    k = args.steps
+    fl = [feats_pinned[i % n_frames] for i in range(k)]
+    ml = [Ms[i % n_frames] for i in range(k)]
+    ol = [outs_pinned[i % n_frames] for i in range(k)]
+    runner.run_host_frames(fl[:max(2, args.warmup)], ml[:max(2, args.warmup)], ol[:max(2, args.warmup)])
+    barrier()
+    t0 = time.perf_counter()
+    runner.run_host_frames(fl, ml, ol)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_fps = frames_per_step * k / e2e_s
+    h2d = feats_pinned[0].numel() * 4 + BN * 36
+    d2h = outs_pinned[0].numel() * 4
+
+    line = None
+    if rank == 0:
+        kb = kernel_breakdown(fusion, ds, device)
+        peak, peak_src = measured_peak_hbm()
+        dom = kb["msda_fused_fwd"]
+        roofline = {"kernel": "msda_fwd_vec4_kernel<16,FUSED> (mvd_msda_fused_fwd_f32), 3 launches/step",
+                    "bound": "hbm", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"],
+                    "timing": "CUDA events on the launch stream, 512 MB L2 flush between launches"}
+        hot_us = kb["warp"]["us"] + LAYERS * dom["us"]
+        cpu = cpu_baseline_leg() if world == 1 else None
+        line = {"metric": "multiview_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "views": BN, "feat": list(feat_shape),
+                           "world_grid": list(ds.Rworld_shape), "layers": LAYERS, "heads": HEADS, "points": POINTS,
+                           "mode": mode, "cuda_graph": True, "tf32": False,
+                           "l2": "2 alternating frame slots; per-step working set ~1.5 GB >> 126 MB L2"},
+                "roofline": roofline,
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "pipeline": "pinned host -> H2D stream / graph replay / D2H stream, 2 slots"},
+                "gpu_launches": (1 + LAYERS) * args.steps,
+                "clocks": clocks,
+                "hot_path": {"warp_us": kb["warp"]["us"], "msda_fused_fwd_us": dom["us"],
+                             "frames_per_sec_kernels_only": 1e6 / hot_us,
+                             "warp_GBps": kb["warp"]["GBps"], "warp_frac": kb["warp"]["GBps"] / peak},
+                "kernels": kb}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,263 @@
+"""Host-side mirror of the callers of the hot path: MSDeformAttn -> DeformableTransformerEncoder(Layer) ->
+DeformTransWorldFeat, with the reference's constructor signatures, forward signatures and state_dict keys, so a
+reference checkpoint loads unchanged (SURVEY 5 "checkpoint").
+
+  MSDeformAttn                       ref: multiview_detector/models/ops/modules/ms_deform_attn.py:31-117
+  DeformableTransformerEncoderLayer  ref: multiview_detector/models/deformable_transformer.py:55-85
+  DeformableTransformerEncoder       ref: multiview_detector/models/deformable_transformer.py:22-52
+  DeformTransWorldFeat               ref: multiview_detector/models/trans_world_feat.py:70-119
+  create_pos_embedding               ref: multiview_detector/models/trans_world_feat.py:15-37
+
+What differs from the reference is only where time went for no reason (SURVEY 3.1 "hot spots (host)"):
+  * pos_embedding, reference_points, spatial_shapes, level_start_index live on the device as non-persistent
+    buffers (the reference re-uploads 16.9 MB + 5.5 MB per frame: deformable_transformer.py:48,
+    trans_world_feat.py:93-95) and the device->host assert of ms_deform_attn.py:94 is done on host ints;
+  * without autograd, the elementwise tail of MSDeformAttn.forward (softmax over L*P, loc = ref + off/(W,H),
+    ms_deform_attn.py:100-107) runs inside the CUDA kernel (ops.msda_fused_forward) reading the compact
+    [Hd*Wd, L, P, 2] reference table instead of its num_cam-fold repeat (mvdetr.py:130);
+  * the whole forward is CUDA-graph capturable (no host syncs, no per-call host->device copies).
+Dense layers (Linear / LayerNorm / Conv2d) stay cuBLAS / cuDNN through torch -- out of the hot-path scope.
+"""
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.init import constant_, normal_, xavier_uniform_
+
+from . import ops
+
+
+def create_pos_embedding(img_size, num_pos_feats=64, temperature=10000, normalize=True, scale=None):
+    """Sine position embedding [1, 2*num_pos_feats, H, W] (values identical to the reference's)."""
+    if scale is not None and normalize is False:
+        raise ValueError("normalize should be True if scale is passed")
+    scale = 2 * math.pi if scale is None else scale
+    H, W = int(img_size[0]), int(img_size[1])
+    ones = torch.ones([1, H, W])
+    y_embed = ones.cumsum(1, dtype=torch.float32)
+    x_embed = ones.cumsum(2, dtype=torch.float32)
+    if normalize:
+        eps = 1e-6
+        y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
+        x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    pos_x = x_embed[:, :, :, None] / dim_t
+    pos_y = y_embed[:, :, :, None] / dim_t
+    pos_x = torch.stack((pos_x[..., 0::2].sin(), pos_x[..., 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[..., 0::2].sin(), pos_y[..., 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+class LevelGeometry:
+    """Host + device copies of (spatial_shapes, level_start_index) made once, so no per-frame upload or readback."""
+
+    def __init__(self, shapes_hw, device):
+        self.hw = [(int(h), int(w)) for h, w in shapes_hw]
+        self.len_in = sum(h * w for h, w in self.hw)
+        self.shapes = torch.as_tensor(self.hw, dtype=torch.long, device=device)
+        starts = np.concatenate([[0], np.cumsum([h * w for h, w in self.hw])[:-1]])
+        self.start = torch.as_tensor(starts, dtype=torch.long, device=device)
+        self.uniform = all(s == self.hw[0] for s in self.hw)
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
+        self.im2col_step = 64
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        constant_(self.sampling_offsets.weight.data, 0.)
+        thetas = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+        grid_init = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(self.n_heads, 1, 1, 2)
+        grid_init = grid_init.repeat(1, self.n_levels, self.n_points, 1)
+        for i in range(self.n_points):
+            grid_init[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(grid_init.view(-1))
+        constant_(self.attention_weights.weight.data, 0.)
+        constant_(self.attention_weights.bias.data, 0.)
+        xavier_uniform_(self.value_proj.weight.data)
+        constant_(self.value_proj.bias.data, 0.)
+        xavier_uniform_(self.output_proj.weight.data)
+        constant_(self.output_proj.bias.data, 0.)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None, geometry=None, ref_table=None):
+        """Reference signature (first six arguments). Extensions used by our encoder: `geometry` (LevelGeometry,
+        avoids the device->host check) and `ref_table` ([Lr,L,P,2] compact reference points: enables the fused
+        kernel when autograd is off)."""
+        N, Len_q, _ = query.shape
+        N, Len_in, _ = input_flatten.shape
+        if geometry is not None:
+            assert geometry.len_in == Len_in
+        else:
+            assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, Len_in, M, self.d_model // M)
+        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
+        attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
+
+        fused = (ref_table is not None and not torch.is_grad_enabled() and value.dtype == torch.float32 and
+                 value.is_cuda)
+        if fused:
+            output = ops.msda_fused_forward(value.contiguous(), input_spatial_shapes, input_level_start_index,
+                                            sampling_offsets.contiguous(), attention_weights.contiguous(), ref_table)
+            return self.output_proj(output)
+
+        attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
+        if reference_points.shape[-1] != 2:
+            raise ValueError("Last dim of reference_points must be 2, but get {} instead.".format(
+                reference_points.shape[-1]))
+        offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
+        if reference_points.dim() == 4:  # upstream Deformable-DETR layout [N, Lq, L, 2]
+            reference_points = reference_points[:, :, :, None, :]
+        sampling_locations = reference_points[:, :, None, :, :, :] \
+            + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+        output = ops.MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
+                                                sampling_locations.contiguous(), attention_weights.contiguous(),
+                                                self.im2col_step)
+        return self.output_proj(output)
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
+                geometry=None, ref_table=None):
+        src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
+                              level_start_index, padding_mask, geometry=geometry, ref_table=ref_table)
+        src = self.norm1(src + self.dropout1(src2))
+        src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
+        return self.norm2(src + self.dropout3(src2))
+
+
+class DeformableTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers, reference_points=None):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+        # reference keeps this as a plain CPU attribute and uploads it every call (deformable_transformer.py:27,48)
+        self.register_buffer("reference_points", reference_points, persistent=False)
+        self.register_buffer("ref_table", None, persistent=False)
+
+    def set_compact_table(self, rows):
+        """If reference_points is `k` identical copies of its first `rows` rows (MVDeTr: mvdetr.py:130), keep the
+        compact [rows, L, P, 2] table for the fused kernel."""
+        rp = self.reference_points
+        if rp is None or rp.dim() != 4 or rp.shape[0] % rows != 0:
+            return False
+        if not torch.equal(rp.view(-1, rows, *rp.shape[1:]), rp[:rows].unsqueeze(0).expand(rp.shape[0] // rows, -1, -1,
+                                                                                           -1, -1)):
+            return False
+        self.ref_table = rp[:rows].contiguous().float()
+        return True
+
+    @staticmethod
+    def get_reference_points(spatial_shapes_hw, valid_ratios, device):
+        refs = []
+        for lvl, (H_, W_) in enumerate(spatial_shapes_hw):
+            ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
+                                          torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device),
+                                          indexing="ij")
+            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+            refs.append(torch.stack((ref_x, ref_y), -1))
+        reference_points = torch.cat(refs, 1)
+        return reference_points[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                geometry=None):
+        output = src
+        if self.reference_points is None:
+            hw = geometry.hw if geometry is not None else spatial_shapes.tolist()
+            reference_points = self.get_reference_points(hw, valid_ratios, device=src.device)
+        else:
+            reference_points = self.reference_points.unsqueeze(0).expand(src.shape[0], -1, -1, -1, -1)
+        for layer in self.layers:
+            output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                           geometry=geometry, ref_table=self.ref_table)
+        return output
+
+
+class DeformTransWorldFeat(nn.Module):
+    def __init__(self, num_cam, Rworld_shape, base_dim, hidden_dim=128, dropout=0.1, nhead=8, dim_feedforward=512,
+                 n_points=4, stride=2, reference_points=None):
+        super().__init__()
+        self.num_cam, self.hidden_dim, self.stride = num_cam, hidden_dim, stride
+        self.Rworld_shape = [int(v) for v in Rworld_shape]
+        self.downsample = nn.Sequential(nn.Conv2d(base_dim, hidden_dim, 3, stride, 1), nn.ReLU())
+        encoder_layer = DeformableTransformerEncoderLayer(hidden_dim, dim_feedforward, dropout, n_levels=num_cam,
+                                                          n_heads=nhead, n_points=n_points)
+        self.encoder = DeformableTransformerEncoder(encoder_layer, 3, reference_points)
+        self.register_buffer("pos_embedding",
+                             create_pos_embedding(np.array(self.Rworld_shape) // stride, hidden_dim // 2),
+                             persistent=False)
+        self.lvl_embedding = nn.Parameter(torch.Tensor(num_cam, hidden_dim))
+        self.merge_linear = nn.Sequential(nn.Conv2d(hidden_dim * num_cam, hidden_dim, 1), nn.ReLU())
+        self.upsample = nn.Sequential(nn.Upsample(self.Rworld_shape, mode="bilinear", align_corners=False),
+                                      nn.Conv2d(hidden_dim, hidden_dim, 3, 1, 1), nn.ReLU())
+        self._reset_parameters()
+        self._geometry = None
+        Hd, Wd = self.pos_embedding.shape[-2:]
+        self.encoder.set_compact_table(Hd * Wd)
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        normal_(self.lvl_embedding)
+
+    def _level_geometry(self, N, H, W, device):
+        g = self._geometry
+        if g is None or g.shapes.device != device or g.hw != [(H, W)] * N:
+            g = self._geometry = LevelGeometry([(H, W)] * N, device)
+        return g
+
+    def forward(self, x, visualize=False):
+        """x [B, N, C, H, W] (any strides; channels-last per view avoids the reference's permute-copy at
+        trans_world_feat.py:92) -> [B, hidden, H, W]. As in the reference only B=1 is valid (its
+        lvl_embedding.view([B, N, 1, C]) at :94)."""
+        B, N, C, H, W = x.shape
+        x = self.downsample(x.reshape(B * N, C, H, W))
+        _, _, H, W = x.shape
+        src_flatten = x.view(B, N, C, H, W).permute(0, 1, 3, 4, 2).reshape(B, N * H * W, C)
+        lvl_pos_embed_flatten = (self.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
+                                 self.lvl_embedding.view([B, N, 1, C])).view([B, N * H * W, C])
+        geo = self._level_geometry(N, H, W, x.device)
+        valid_ratios = None if self.encoder.reference_points is not None else torch.ones([B, N, 2], device=x.device)
+        memory = self.encoder(src_flatten, geo.shapes, geo.start, valid_ratios, lvl_pos_embed_flatten, geometry=geo)
+        merged_feat = self.merge_linear(memory.view(B, N, H, W, C).permute(0, 1, 4, 2, 3).reshape(B, N * C, H, W))
+        return self.upsample(merged_feat)

@@ -150,43 +150,7 @@ def gen_mvdetr_mini():
          out=o, grad_value=gv, grad_loc=gl, grad_attn=ga)
 
 
-class _MiniBase:
-    pass
-
-
-def mini_dataset(num_cam=3, Rworld=(24, 40), Rimg=(18, 32), world_reduce=4, img_reduce=12, seed=0):
-    """Synthetic stand-in for frameDataset/Wildtrack exposing the attributes mvdetr.py:34,46-56,78-95 read:
-    ring of pinhole cameras looking at the centre of a ground plane of (Rworld*world_reduce) cells of 2.5 cm."""
-    rng = np.random.RandomState(seed)
-    base = _MiniBase()
-    cell = 2.5  # cm per grid cell, as Wildtrack.py:30-32
-    nrow, ncol = Rworld[0] * world_reduce, Rworld[1] * world_reduce
-    base.worldcoord_unit = 0.01  # cm -> m
-    base.indexing = "ij"
-    base.world_indexing_from_xy_mat = np.array([[0, 1, 0], [1, 0, 0], [0, 0, 1]], dtype=float)
-    base.worldcoord_from_worldgrid_mat = np.array([[0, cell, -ncol * cell / 2], [cell, 0, -nrow * cell / 2], [0, 0, 1]])
-    H_img, W_img = Rimg[0] * img_reduce, Rimg[1] * img_reduce
-    Ks, Rts = [], []
-    for cam in range(num_cam):
-        ang = 2 * np.pi * cam / num_cam + rng.uniform(-0.2, 0.2)
-        radius = 0.9 * max(nrow, ncol) * cell
-        eye = np.array([radius * np.cos(ang), radius * np.sin(ang), rng.uniform(250.0, 400.0)])
-        target = np.array([rng.uniform(-20, 20), rng.uniform(-20, 20), 0.0])
-        fwd = (target - eye) / np.linalg.norm(target - eye)
-        right = np.cross(fwd, [0, 0, 1.0])
-        right /= np.linalg.norm(right)
-        down = np.cross(fwd, right)
-        R = np.stack([right, down, fwd])
-        t = -R @ eye
-        f = 0.9 * W_img
-        Ks.append(np.array([[f, 0, W_img / 2], [0, f, H_img / 2], [0, 0, 1.0]]))
-        Rts.append(np.concatenate([R, t[:, None]], 1))
-    base.intrinsic_matrices, base.extrinsic_matrices = Ks, Rts
-    ds = _MiniBase()
-    ds.base, ds.num_cam = base, num_cam
-    ds.Rworld_shape, ds.Rimg_shape = list(Rworld), list(Rimg)
-    ds.world_reduce, ds.img_reduce = world_reduce, img_reduce
-    return ds
+from mvdetr_b200.synthetic import mini_scene as mini_dataset  # noqa: E402  (scene generator shared with the tests)
 
 
 def gen_world_feat_mini():

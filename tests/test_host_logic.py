@@ -45,3 +45,23 @@ def test_warp_argument_errors():
         ops.warp_perspective(src, M[:1], (4, 5), align_corners=False)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.warp_perspective(src, M, (4, 5), align_corners=False)
+
+
+def test_mirror_loads_reference_state_dict_and_projection_chain(golden):
+    """CPU: parameter names of the mirror are the reference's (strict load of a reference state_dict), buffers stay out
+    of the state_dict, and the projection / reference-map helpers reproduce the reference's numbers."""
+    import numpy as np
+    from mvdetr_b200 import projection, synthetic
+    from mvdetr_b200.world_feat import DeformTransWorldFeat
+    g = golden("world_feat_mini.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g if k.startswith("sd.")}
+    N, C = g["imgs_feat"].shape[:2]
+    model = DeformTransWorldFeat(N, list(g["Rworld"]), C, hidden_dim=C, nhead=int(g["nhead"]), dim_feedforward=64,
+                                 reference_points=torch.from_numpy(g["ref_points"]))
+    model.load_state_dict(sd, strict=True)
+    assert set(model.state_dict()) == set(sd)
+    ds = synthetic.mini_scene()
+    assert np.array_equal(projection.world_grid_projection_mats(ds).numpy(), g["proj_mats64"])
+    ref = projection.create_reference_map(ds, 4).repeat([N, 1, 1, 1])
+    assert torch.equal(ref, torch.from_numpy(g["ref_points"]))
+    assert model.encoder.ref_table.shape[0] * N == ref.shape[0]

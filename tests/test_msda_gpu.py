@@ -1,0 +1,204 @@
+"""GPU parity tests for multi-scale deformable attention: CUDA (through the C ABI) vs the CPU oracle, the committed
+golden vectors produced by the reference's Python core, the reference's own CUDA op (when oracle/_ref was built),
+and size-independent properties at BASELINE.json's full Wildtrack size."""
+import numpy as np
+import pytest
+import torch
+
+from mvdetr_b200 import ops
+from oracle import cpu_oracle as co
+from tests.gpu_util import dev, make_problem, ref_cuda_ext, viewgrid_problem
+
+pytestmark = pytest.mark.gpu
+
+FP32_ATOL = 1e-4  # BASELINE.json north_star: "within 1e-4 fp32"
+
+
+def run_fwd(value, shapes, start, loc, attn, step=64):
+    return ops.MSDeformAttnFunction.apply(value, shapes, start, loc, attn, step)
+
+
+def test_reference_opstest_forward_double_and_float(golden, cuda):
+    """ops/test.py:31-60 with the reference's shapes, seed and tolerances, against the reference core's outputs."""
+    g = golden("msda_opstest.npz")
+    shapes, start = dev(g["shapes"], cuda), dev(g["start"], cuda)
+    o64 = run_fwd(dev(g["value_f64"], cuda), shapes, start, dev(g["loc_f64"], cuda), dev(g["attn_f64"], cuda), 2)
+    assert torch.allclose(o64.cpu(), torch.from_numpy(g["out_f64"]))  # rtol 1e-5, atol 1e-8
+    o32 = run_fwd(dev(g["value_f32"], cuda), shapes, start, dev(g["loc_f32"], cuda), dev(g["attn_f32"], cuda), 2)
+    assert torch.allclose(o32.cpu(), torch.from_numpy(g["out_f32"]), rtol=1e-2, atol=1e-3)
+    assert (o32.cpu() - torch.from_numpy(g["out_f32"])).abs().max() <= FP32_ATOL
+
+
+@pytest.mark.parametrize("name", ["msda_config1.npz", "msda_mvdetr_mini.npz", "msda_ragged.npz"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_golden_forward_backward(golden, cuda, name, dtype):
+    g = golden(name)
+    value, loc, attn, go = (dev(g[k], cuda, dtype) for k in ("value", "loc", "attn", "grad_out"))
+    shapes, start = dev(g["shapes"], cuda), dev(g["start"], cuda)
+    value.requires_grad_(True), loc.requires_grad_(True), attn.requires_grad_(True)
+    out = run_fwd(value, shapes, start, loc, attn)
+    out.backward(go)
+    if dtype == torch.float64:
+        tol = dict(rtol=1e-9, atol=1e-10)
+    else:
+        tol = dict(rtol=0, atol=FP32_ATOL)
+    assert np.allclose(out.detach().cpu().numpy(), g["out"], **tol)
+    # gradients are sums of up to Lq*M*L*P*4 atomics per element; fp32 tolerance scales with their magnitude
+    for got, key in ((value.grad, "grad_value"), (loc.grad, "grad_loc"), (attn.grad, "grad_attn")):
+        ref = g[key]
+        scale = max(1.0, float(np.abs(ref).max()))
+        err = np.abs(got.cpu().numpy() - ref).max()
+        assert err <= (1e-9 if dtype == torch.float64 else FP32_ATOL) * scale, (key, err)
+
+
+@pytest.mark.parametrize("D", [16, 30, 32, 64, 71, 1025, 2048, 3096])
+def test_reference_gradcheck_contract(cuda, D):
+    """ops/test.py:63-86: fp64 gradcheck on the reference's D list (every reference backward variant) plus D=16."""
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=cuda)
+    start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = 30
+    torch.manual_seed(3)
+    value = (torch.rand(N, S, M, D) * 0.01).double().to(cuda).requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).double().to(cuda).requires_grad_(True)
+    attn = torch.rand(N, Lq, M, L, P) + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().to(cuda).requires_grad_(True)
+    assert torch.autograd.gradcheck(ops.MSDeformAttnFunction.apply, (value, shapes, start, loc, attn, 2),
+                                    nondet_tol=1e-9)
+
+
+@pytest.mark.parametrize("D,M,P", [(4, 3, 2), (8, 8, 4), (16, 8, 4), (32, 8, 8), (64, 2, 4), (128, 1, 3), (12, 2, 4),
+                                   (7, 3, 1)])
+def test_seeded_random_vs_c_oracle_fp32(cuda, D, M, P):
+    """Every vec4 instantiation and the scalar fallback, ragged levels, B=2 (B > im2col_step exercised below)."""
+    shapes_list = [(13, 17), (7, 9), (4, 5), (1, 1)]
+    prob = make_problem(2, shapes_list, M, D, 37, P, seed=100 + D)
+    value, shapes, start, loc, attn, go = (t.to(cuda) for t in prob)
+    value.requires_grad_(True), loc.requires_grad_(True), attn.requires_grad_(True)
+    out = run_fwd(value, shapes, start, loc, attn)
+    out.backward(go)
+    n = [t.detach().cpu().numpy() for t in prob]
+    ref = co.msda_forward(n[0], n[1], n[2], n[3], n[4])
+    assert np.abs(out.detach().cpu().numpy() - ref).max() <= FP32_ATOL
+    gv, gl, ga = co.msda_backward(n[5], n[0], n[1], n[2], n[3], n[4])
+    for got, want in ((value.grad, gv), (loc.grad, gl), (attn.grad, ga)):
+        scale = max(1.0, float(np.abs(want).max()))
+        assert np.abs(got.cpu().numpy() - want).max() <= FP32_ATOL * scale
+
+
+def test_im2col_step_semantics(cuda):
+    """batch % min(batch, im2col_step) must be 0 (ms_deform_attn_cuda.cu:50-52); chunking never changes results."""
+    prob = [t.to(cuda) for t in make_problem(4, [(5, 6)], 2, 16, 9, 4, seed=5)]
+    a = run_fwd(*prob[:5], 64)
+    b = run_fwd(*prob[:5], 2)
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="must divide"):
+        run_fwd(*prob[:5], 3)
+
+
+def test_error_behaviour_on_gpu(cuda):
+    prob = [t.to(cuda) for t in make_problem(1, [(5, 6)], 2, 16, 9, 4, seed=5)]
+    with pytest.raises(RuntimeError, match="contiguous"):
+        run_fwd(prob[0].transpose(1, 2).contiguous().transpose(1, 2), *prob[1:5])
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        run_fwd(prob[0], prob[1].cpu(), *prob[2:5])
+    with pytest.raises(RuntimeError, match="not implemented for"):
+        run_fwd(prob[0].half(), prob[1], prob[2], prob[3].half(), prob[4].half())
+
+
+def test_all_samples_outside_give_exact_zero(cuda):
+    value, shapes, start, loc, attn, _ = (t.to(cuda) for t in make_problem(1, [(6, 7), (3, 3)], 4, 16, 11, 4, seed=9))
+    out = run_fwd(value, shapes, start, loc + 3.0, attn)
+    assert torch.count_nonzero(out) == 0
+
+
+def test_matches_reference_cuda_extension(cuda):
+    """On-GPU parity with the reference's own CUDA op (built from its sources for sm_100a into oracle/_ref)."""
+    ext = ref_cuda_ext()
+    if ext is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    value, shapes, start, loc, attn, go = (t.to(cuda) for t in viewgrid_problem(7, 30, 45, 8, 16, 4, seed=1))
+    ours = ops.ms_deform_attn_forward(value, shapes, start, loc, attn, 64)
+    theirs = ext.ms_deform_attn_forward(value, shapes, start, loc, attn, 64)
+    assert (ours - theirs).abs().max().item() <= FP32_ATOL
+    g_ours = ops.ms_deform_attn_backward(value, shapes, start, loc, attn, go, 64)
+    g_theirs = ext.ms_deform_attn_backward(value, shapes, start, loc, attn, go, 64)
+    for a, b in zip(g_ours, g_theirs):
+        assert (a - b).abs().max().item() <= FP32_ATOL * max(1.0, b.abs().max().item())
+    # fp64 too
+    o64 = ops.ms_deform_attn_forward(value.double(), shapes, start, loc.double(), attn.double(), 64)
+    t64 = ext.ms_deform_attn_forward(value.double(), shapes, start, loc.double(), attn.double(), 64)
+    assert torch.allclose(o64, t64, rtol=1e-10, atol=1e-12)
+
+
+def test_full_wildtrack_size_properties(cuda):
+    """BASELINE config 2 size (Lq = S = 75600, M=8, D=16, L=7, P=4): properties that need no CPU reference.
+    (a) constant value field and in-range samples => out = const * sum(attn) = const;
+    (b) linearity in value and in attn;
+    (c) a strided sample of queries agrees with the C oracle."""
+    L, H, W, M, D, P = 7, 60, 180, 8, 16, 4
+    value, shapes, start, loc, attn, _ = (t.to(cuda) for t in viewgrid_problem(L, H, W, M, D, P, seed=2))
+    out = run_fwd(value, shapes, start, loc, attn)
+    assert out.shape == (1, L * H * W, M * D) and torch.isfinite(out).all()
+    # (a) interior queries only (their +-4 px samples stay inside the map)
+    const = torch.full_like(value, 0.75)
+    oc = run_fwd(const, shapes, start, loc.clamp(0.1, 0.9), attn)
+    assert (oc - 0.75).abs().max().item() <= 1e-5
+    # (b)
+    v2 = torch.randn_like(value)
+    lhs = run_fwd(value * 0.5 + v2 * 2.0, shapes, start, loc, attn)
+    rhs = out * 0.5 + run_fwd(v2, shapes, start, loc, attn) * 2.0
+    assert (lhs - rhs).abs().max().item() <= 1e-4
+    assert (run_fwd(value, shapes, start, loc, attn * 3.0) - out * 3.0).abs().max().item() <= 1e-4
+    # (c) every 997th query through the C oracle
+    idx = torch.arange(0, L * H * W, 997, device=cuda)
+    ref = co.msda_forward(value.cpu().numpy(), shapes.cpu().numpy(), start.cpu().numpy(),
+                          loc[:, idx].cpu().numpy(), attn[:, idx].cpu().numpy())
+    assert np.abs(out[:, idx].cpu().numpy() - ref).max() <= FP32_ATOL
+
+
+def test_full_wildtrack_size_backward_properties(cuda):
+    """Backward at full size: sum of grad_value equals sum over samples of attn*grad_out*(in-range bilinear weights),
+    checked through <grad_value, 1> = d/dt out(value + t*1) . grad_out, plus an oracle check on a query sample."""
+    L, H, W, M, D, P = 7, 60, 180, 8, 16, 4
+    value, shapes, start, loc, attn, go = (t.to(cuda) for t in viewgrid_problem(L, H, W, M, D, P, seed=3))
+    gv, gl, ga = ops.ms_deform_attn_backward(value, shapes, start, loc, attn, go, 64)
+    ones = torch.ones_like(value)
+    directional = (run_fwd(ones, shapes, start, loc, attn) * go).sum().item()  # out is linear in value
+    assert abs(gv.sum().item() - directional) <= 1e-3 * max(1.0, abs(directional))
+    # grad_attn[q,m,l,p] = <grad_out[q,m,:], bilinear(value)>  =>  sum_lp attn*grad_attn = <grad_out, out>
+    out = run_fwd(value, shapes, start, loc, attn)
+    lhs = (attn * ga).sum().item()
+    rhs = (out * go).sum().item()
+    assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(rhs))
+    idx = torch.arange(0, L * H * W, 1999, device=cuda)
+    n = lambda t: t.cpu().numpy()  # noqa: E731
+    _, gl_ref, ga_ref = co.msda_backward(n(go[:, idx]), n(value), n(shapes), n(start), n(loc[:, idx]), n(attn[:, idx]))
+    assert np.abs(n(gl[:, idx]) - gl_ref).max() <= FP32_ATOL * max(1.0, np.abs(gl_ref).max())
+    assert np.abs(n(ga[:, idx]) - ga_ref).max() <= FP32_ATOL * max(1.0, np.abs(ga_ref).max())
+
+
+def test_fused_entry_point_matches_module_arithmetic(golden, cuda):
+    """mvd_msda_fused_fwd_f32 vs the reference module's own loc/softmax arithmetic + core (golden from the reference)."""
+    m = golden("msda_module_mini.npz")
+    value, offsets, logits, ref = (dev(m[k], cuda) for k in ("value", "offsets", "logits", "ref_table"))
+    shapes, start = dev(m["shapes"], cuda), dev(m["start"], cuda)
+    out, attn, loc = ops.msda_fused_forward(value, shapes, start, offsets, logits, ref, want_aux=True)
+    assert np.abs(out.cpu().numpy() - m["core_out"]).max() <= FP32_ATOL
+    assert np.abs(attn.cpu().numpy() - m["attn"]).max() <= 1e-6
+    assert np.abs(loc.cpu().numpy() - m["loc"]).max() <= 1e-6
+    out2 = ops.msda_fused_forward(value, shapes, start, offsets, logits, ref)
+    assert torch.equal(out, out2)
+
+
+def test_host_buffer_entry_point(cuda):
+    """The *_host C entry point (used for e2e timing) gives the same bytes as the device entry point."""
+    from mvdetr_b200 import _C
+    prob = make_problem(1, [(9, 11), (5, 6)], 8, 16, 50, 4, seed=21)
+    value, shapes, start, loc, attn, _ = prob
+    out_host = torch.empty(1, 50, 128)
+    rc = _C.lib.mvd_msda_fwd_f32_host(value.data_ptr(), shapes.data_ptr(), start.data_ptr(), loc.data_ptr(),
+                                      attn.data_ptr(), 1, value.shape[1], 8, 16, 2, 50, 4, out_host.data_ptr(), None)
+    assert rc == 0, _C.error_string(rc)
+    out_dev = run_fwd(*(t.to(cuda) for t in prob[:5]))
+    assert torch.equal(out_host, out_dev.cpu())
