@@ -160,6 +160,16 @@ MVD_API int mvd_warp_bwd_f32(const float* grad_dst, const float* Mat,
                      float* grad_src, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused residual add + LayerNorm over the last dimension (caller-side glue of the encoder layer, eval mode):
+ *   out[r,:] = LayerNorm(x[r,:] + res[r,:]; eps) * gamma + beta          res may be NULL (plain LayerNorm)
+ *   replaces `src = self.norm1(src + self.dropout1(src2))` / `self.norm2(src + self.dropout3(src2))`
+ *       ref: mvd/models/deformable_transformer.py:79-80,84-85
+ *   x, res, out [rows, C] (out may alias x or res); gamma, beta [C]; C % 4 == 0, C <= 1024, 16-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_add_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
+                                  int64_t rows, int C, float eps, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (used for end-to-end timing and by non-PyTorch callers):
  * same arguments, but every pointer is HOST memory (pinned or pageable). They allocate device
  * scratch, copy in, run the kernel above, copy the result back and synchronise `stream` before

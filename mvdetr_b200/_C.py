@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmvdetr_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"mvdetr_b200: CUDA library not built ({LIB_PATH} missing). Build it with `python -m mvdetr_b200.build` "
+        f"mvdetr_b200: CUDA library not built ({LIB_PATH} missing). Build it with `python mvdetr_b200/build.py` "
         "(needs nvcc; there is deliberately no CPU or PyTorch fallback).")
 
 lib = ctypes.CDLL(LIB_PATH)
@@ -28,6 +28,7 @@ SIGNATURES = {
     "mvd_msda_bwd_f64": [_p] * 6 + [_i] * 7 + [_p] * 4,
     "mvd_msda_fwd_viewgrid_f32": [_p] * 3 + [_i] * 8 + [_p, _p],
     "mvd_msda_fused_fwd_f32": [_p] * 6 + [_i] * 8 + [_p] * 4,
+    "mvd_add_layernorm_f32": [_p] * 4 + [ctypes.c_int64, _i, ctypes.c_float, _p, _p],
     "mvd_warp_fwd_f32": [_p, _p] + [_i] * 6 + [_p, _i, _p],
     "mvd_warp_bwd_f32": [_p, _p] + [_i] * 6 + [_p, _p],
     "mvd_msda_fwd_f32_host": [_p] * 5 + [_i] * 7 + [_p, _p],

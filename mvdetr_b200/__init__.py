@@ -6,11 +6,11 @@ reference's operator interface (ops.py), its encoder callers (world_feat.py), th
 CPU fallback.
 """
 from . import _C  # noqa: F401  (raises ImportError with build instructions if the .so is missing)
-from .ops import (MSDeformAttnFunction, ms_deform_attn_backward, ms_deform_attn_forward, msda_fused_forward,
+from .ops import (MSDeformAttnFunction, add_layer_norm, ms_deform_attn_backward, ms_deform_attn_forward, msda_fused_forward,
                   msda_viewgrid_forward, warp_perspective)
 
 __all__ = ["MSDeformAttnFunction", "ms_deform_attn_forward", "ms_deform_attn_backward", "msda_fused_forward",
-           "msda_viewgrid_forward", "warp_perspective", "install_shims"]
+           "msda_viewgrid_forward", "warp_perspective", "add_layer_norm", "install_shims"]
 
 __version__ = "0.1.0"
 

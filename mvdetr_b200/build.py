@@ -1,6 +1,7 @@
 """Build recipe for libmvdetr_b200.so (hand-written CUDA for sm_100a behind the C ABI in include/mvdetr_b200.h).
 
-Run `python -m mvdetr_b200.build` (or `__graft_entry__.build()`). nvcc cross-compiles without a GPU.
+Run `python mvdetr_b200/build.py` (or `__graft_entry__.build()`); the file is loaded by path, never through the
+package, because importing the package requires the library this script produces. nvcc cross-compiles without a GPU.
 The library links cudart statically and has no torch / libcuda link-time dependency, so it loads on a CPU-only
 box (the symbol-export test relies on that).
 """
@@ -13,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvdetr_b200.so")
-SOURCES = ["capi.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_viewgrid.cu", "warp.cu"]
+SOURCES = ["capi.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_viewgrid.cu", "warp.cu", "layernorm.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

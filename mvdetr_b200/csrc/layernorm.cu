@@ -1,0 +1,97 @@
+// Fused residual add + LayerNorm over the last dimension: out[r,:] = LN(x[r,:] + res[r,:]) * gamma + beta.
+// The encoder layer does this twice per layer on [N*Hd*Wd, C] tokens (eval mode, dropout = identity):
+//   ref: multiview_detector/models/deformable_transformer.py:79-80 and :84-85
+// torch runs it as an elementwise add (3 x 38.7 MB of traffic) plus a LayerNorm kernel with one 128-thread block
+// per 128-float row (measured 15 + 114 us at Wildtrack size, profiles/r01_launches.md); here one warp owns a row,
+// keeps it in registers (float4 per lane per 128 channels), and the tensor is read and written once.
+#include "common.cuh"
+
+namespace mvd {
+
+template <int VPL>  // float4 vectors per lane: C <= 128 * VPL
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int64_t rows, int C,
+                                                            float eps, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  const float4* rr = res ? reinterpret_cast<const float4*>(res + row * C) : nullptr;
+  float4 v[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nvec) {
+      v[k] = __ldcs(xr + i);
+      if (rr) {
+        const float4 r = __ldcs(rr + i);
+        v[k].x += r.x;
+        v[k].y += r.y;
+        v[k].z += r.z;
+        v[k].w += r.w;
+      }
+      sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    if (lane + 32 * k < nvec) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.f / sqrtf(sq / (float)C + eps);
+  float4* orow = reinterpret_cast<float4*>(out + row * C);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      orow[i] = o;
+    }
+  }
+}
+
+}  // namespace mvd
+
+using namespace mvd;
+
+extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
+                                     int64_t rows, int C, float eps, float* out, void* stream) {
+  if (!x || !gamma || !beta || !out) return MVD_ERR_NULL_POINTER;
+  if (rows <= 0 || C <= 0) return MVD_ERR_BAD_SHAPE;
+  if ((C & 3) || C > 1024) return MVD_ERR_UNSUPPORTED;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                       reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                       (res ? reinterpret_cast<uintptr_t>(res) : 0);
+  if (al & 15u) return MVD_ERR_MISALIGNED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t blocks = ceil_div64(rows, 8);
+  if (blocks > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
+  if (C <= 128)
+    add_layernorm_kernel<1><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+  else if (C <= 256)
+    add_layernorm_kernel<2><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+  else if (C <= 512)
+    add_layernorm_kernel<4><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+  else
+    add_layernorm_kernel<8><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}

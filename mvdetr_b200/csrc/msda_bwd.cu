@@ -108,6 +108,14 @@ __global__ void __launch_bounds__(256) msda_bwd_scalar_kernel(
   }
 }
 
+// vec4 path. Per chunk of C = min(G, 8) samples of one (b,q,m) pair (G = D/4 lanes):
+//   prep    : lane j < C evaluates sample s0+j once (loc, attn -> fractional weights, packed pixel index + mask);
+//   scatter : the group walks the C samples (values arrive by width-G shuffles); each lane loads its 4 channels of the
+//             4 corners, issues one red.global.add.v4.f32 per valid corner and keeps 3 partial sums per sample;
+//   reduce  : butterfly over lane strides >= C, then a transpose-reduction over the low bits, so that lane j ends up
+//             with the three totals of sample s0+j and writes them (coalesced 8 B / 4 B stores, no atomics).
+constexpr int kPxBiasB = 1 << 27;
+
 template <int D>
 __global__ void __launch_bounds__(256) msda_bwd_vec4_kernel(
     const float* __restrict__ grad_out, const float* __restrict__ value, const int64_t* __restrict__ shapes,
@@ -115,7 +123,9 @@ __global__ void __launch_bounds__(256) msda_bwd_vec4_kernel(
     int L, int Lq, int P, int64_t n_pairs, float* __restrict__ grad_value, float* __restrict__ grad_loc,
     float* __restrict__ grad_attn) {
   constexpr int G = D / 4;
+  constexpr int C = G < 8 ? G : 8;
   constexpr int PAIRS = 256 / G;
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ Level s_lvl[];
   load_levels(s_lvl, shapes, start, L);
   __syncthreads();
@@ -129,67 +139,107 @@ __global__ void __launch_bounds__(256) msda_bwd_vec4_kernel(
   const int LP = L * P;
   const int64_t stride_px = (int64_t)M * D;
   const int64_t voff = (b * S * M + m) * (int64_t)D + sub * 4;
-  const float* lp = loc + pair * LP * 2;
+  const float2* lp = reinterpret_cast<const float2*>(loc) + pair * LP;
   const float* ap = attn + pair * LP;
   float2* glp = reinterpret_cast<float2*>(grad_loc) + pair * LP;
   float* gap = grad_attn + pair * LP;
   const float4 g = __ldg(reinterpret_cast<const float4*>(grad_out + pair * D + sub * 4));
 
-  for (int l = 0; l < L; ++l) {
-    const Level lv = s_lvl[l];
-    const int64_t loff = voff + (int64_t)lv.start * stride_px;
-    const float fH = (float)lv.H, fW = (float)lv.W;
-    for (int p = 0; p < P; ++p) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(lp));
-      const float a = __ldg(ap);
-      lp += 2;
-      ap += 1;
+  int gl = 0, gp = 0;
+  for (int s0 = 0; s0 < LP; s0 += C) {
+    // ---- prep ----
+    const int s = s0 + sub;
+    float lh = 0.f, lw = 0.f, a = 0.f;
+    unsigned code = 0u;
+    if (sub < C && s < LP) {
+      const Level lv = s_lvl[s / P];
+      const float fH = (float)lv.H, fW = (float)lv.W;
+      const float2 xy = ld_stream2(reinterpret_cast<const float*>(lp + s));
+      a = ld_stream(ap + s);
       const float h_im = __fsub_rn(__fmul_rn(xy.y, fH), 0.5f);
       const float w_im = __fsub_rn(__fmul_rn(xy.x, fW), 0.5f);
-      float gw = 0.f, gh = 0.f, ga = 0.f;
       if (h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW) {
         const float hf = floorf(h_im), wf = floorf(w_im);
         const int h0 = (int)hf, w0 = (int)wf;
-        const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-        const bool top = h0 >= 0, bot = h0 + 1 <= lv.H - 1, lef = w0 >= 0, rig = w0 + 1 <= lv.W - 1;
-        const int64_t o00 = loff + ((int64_t)h0 * lv.W + w0) * stride_px;
+        lh = h_im - hf;
+        lw = w_im - wf;
+        const unsigned top = h0 >= 0, bot = h0 + 1 <= lv.H - 1, lef = w0 >= 0, rig = w0 + 1 <= lv.W - 1;
+        const unsigned mask = (top & lef) | ((top & rig) << 1) | ((bot & lef) << 2) | ((bot & rig) << 3);
+        code = (unsigned)(lv.start + h0 * lv.W + w0 + kPxBiasB) | (mask << 28);
+      }
+    }
+    // ---- scatter + partial sums ----
+    float pw[C], ph[C], pa[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      pw[j] = ph[j] = pa[j] = 0.f;
+      const unsigned cj = __shfl_sync(FULL, code, j, G);
+      const float jlh = __shfl_sync(FULL, lh, j, G);
+      const float jlw = __shfl_sync(FULL, lw, j, G);
+      const float ja = __shfl_sync(FULL, a, j, G);
+      if (cj >> 28) {
+        const Level lv = s_lvl[gl];
+        const int64_t o00 = voff + (int64_t)((int)(cj & 0x0fffffffu) - kPxBiasB) * stride_px;
         const int64_t o01 = o00 + stride_px;
         const int64_t o10 = o00 + (int64_t)lv.W * stride_px;
         const int64_t o11 = o10 + stride_px;
+        const bool c1 = cj & (1u << 28), c2 = cj & (2u << 28), c3 = cj & (4u << 28), c4 = cj & (8u << 28);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 v1 = (top && lef) ? __ldg(reinterpret_cast<const float4*>(value + o00)) : z;
-        const float4 v2 = (top && rig) ? __ldg(reinterpret_cast<const float4*>(value + o01)) : z;
-        const float4 v3 = (bot && lef) ? __ldg(reinterpret_cast<const float4*>(value + o10)) : z;
-        const float4 v4 = (bot && rig) ? __ldg(reinterpret_cast<const float4*>(value + o11)) : z;
-        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-        const float4 tg = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+        const float4 v1 = c1 ? __ldg(reinterpret_cast<const float4*>(value + o00)) : z;
+        const float4 v2 = c2 ? __ldg(reinterpret_cast<const float4*>(value + o01)) : z;
+        const float4 v3 = c3 ? __ldg(reinterpret_cast<const float4*>(value + o10)) : z;
+        const float4 v4 = c4 ? __ldg(reinterpret_cast<const float4*>(value + o11)) : z;
+        const float hh = 1.f - jlh, hw = 1.f - jlw;
+        const float w1 = hh * hw, w2 = hh * jlw, w3 = jlh * hw, w4 = jlh * jlw;
+        const float4 tg = make_float4(g.x * ja, g.y * ja, g.z * ja, g.w * ja);
         if (valid) {
-          if (top && lef) red_add4(grad_value + o00, w1 * tg.x, w1 * tg.y, w1 * tg.z, w1 * tg.w);
-          if (top && rig) red_add4(grad_value + o01, w2 * tg.x, w2 * tg.y, w2 * tg.z, w2 * tg.w);
-          if (bot && lef) red_add4(grad_value + o10, w3 * tg.x, w3 * tg.y, w3 * tg.z, w3 * tg.w);
-          if (bot && rig) red_add4(grad_value + o11, w4 * tg.x, w4 * tg.y, w4 * tg.z, w4 * tg.w);
+          if (c1) red_add4(grad_value + o00, w1 * tg.x, w1 * tg.y, w1 * tg.z, w1 * tg.w);
+          if (c2) red_add4(grad_value + o01, w2 * tg.x, w2 * tg.y, w2 * tg.z, w2 * tg.w);
+          if (c3) red_add4(grad_value + o10, w3 * tg.x, w3 * tg.y, w3 * tg.z, w3 * tg.w);
+          if (c4) red_add4(grad_value + o11, w4 * tg.x, w4 * tg.y, w4 * tg.z, w4 * tg.w);
         }
-#define MVD_CH(C)                                                                 \
-  ga += g.C * (w1 * v1.C + w2 * v2.C + w3 * v3.C + w4 * v4.C);                     \
-  gw += (hh * (v2.C - v1.C) + lh * (v4.C - v3.C)) * tg.C;                          \
-  gh += (hw * (v3.C - v1.C) + lw * (v4.C - v2.C)) * tg.C;
+        float sa = 0.f, sw = 0.f, sh = 0.f;
+#define MVD_CH(X)                                                      \
+  sa += g.X * (w1 * v1.X + w2 * v2.X + w3 * v3.X + w4 * v4.X);          \
+  sw += (hh * (v2.X - v1.X) + jlh * (v4.X - v3.X)) * tg.X;              \
+  sh += (hw * (v3.X - v1.X) + jlw * (v4.X - v2.X)) * tg.X;
         MVD_CH(x) MVD_CH(y) MVD_CH(z) MVD_CH(w)
 #undef MVD_CH
-        gw *= fW;
-        gh *= fH;
+        pa[j] = sa;
+        pw[j] = sw * (float)lv.W;
+        ph[j] = sh * (float)lv.H;
       }
+      if (++gp == P) {
+        gp = 0;
+        ++gl;
+      }
+    }
+    // ---- reduce: lanes with equal (sub mod C) first, then transpose over the low bits ----
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {
-        gw += __shfl_xor_sync(0xffffffffu, gw, o, G);
-        gh += __shfl_xor_sync(0xffffffffu, gh, o, G);
-        ga += __shfl_xor_sync(0xffffffffu, ga, o, G);
+    for (int o = G / 2; o >= C; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        pw[j] += __shfl_xor_sync(FULL, pw[j], o, G);
+        ph[j] += __shfl_xor_sync(FULL, ph[j], o, G);
+        pa[j] += __shfl_xor_sync(FULL, pa[j], o, G);
       }
-      if (sub == 0 && valid) {
-        *glp = make_float2(gw, gh);
-        *gap = ga;
+    }
+#pragma unroll
+    for (int o = C / 2; o > 0; o >>= 1) {
+      const bool upper = sub & o;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const float sw = upper ? pw[i] : pw[i + o], kw = upper ? pw[i + o] : pw[i];
+        const float sh = upper ? ph[i] : ph[i + o], kh = upper ? ph[i + o] : ph[i];
+        const float sa = upper ? pa[i] : pa[i + o], ka = upper ? pa[i + o] : pa[i];
+        pw[i] = kw + __shfl_xor_sync(FULL, sw, o, G);
+        ph[i] = kh + __shfl_xor_sync(FULL, sh, o, G);
+        pa[i] = ka + __shfl_xor_sync(FULL, sa, o, G);
       }
-      glp += 1;
-      gap += 1;
+    }
+    if (sub < C && s < LP && valid) {
+      glp[s] = make_float2(pw[0], ph[0]);
+      gap[s] = pa[0];
     }
   }
 }
@@ -239,7 +289,8 @@ extern "C" int mvd_msda_bwd_f32(const float* grad_out, const float* value, const
   if (B <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq <= 0 || P <= 0 || L > 4096) return MVD_ERR_BAD_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   MVD_CUDA_TRY(cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)B * S * M * D, st));
-  const bool fast = al16(grad_out) && al16(value) && al16(grad_value) && al8(loc) && al8(grad_loc);
+  const bool fast = al16(grad_out) && al16(value) && al16(grad_value) && al8(loc) && al8(grad_loc) &&
+                    2 * (int64_t)S + 2 <= (int64_t)kPxBiasB;
   if (fast) {
 #define MVD_CASE(DD)                                                                                             \
   case DD:                                                                                                       \

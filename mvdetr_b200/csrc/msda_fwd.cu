@@ -68,9 +68,18 @@ __global__ void __launch_bounds__(256) msda_fwd_scalar_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// vec4 path: D/4 lanes per (b,q,m) pair, 128-bit corner loads
+// vec4 path: G = D/4 lanes own one (b,q,m) pair. Work is split in two phases per chunk of G samples:
+//   prep   : lane j of the group evaluates sample (s0 + j) -- loads its loc/attn (or offset/logit/ref when FUSED)
+//            exactly once (no broadcast loads), and reduces it to 4 attention-scaled corner weights plus one
+//            packed word (top-left pixel index + 4 corner-valid bits);
+//   gather : the group walks the G samples; the 5 words come from the owning lane by width-G shuffles, every lane
+//            issues one predicated 128-bit load per corner (a D=16 head-pixel = 64 B = 4 lanes) and 16 FMAs.
+// Measured motivation (profiles/r01_*): the first version recomputed the sample arithmetic in all G lanes and was
+// issue-bound (72 % issue-active, 182 warp-instructions per 8 samples).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+constexpr int kPxBias = 1 << 27;  // packed pixel index = px + kPxBias in the low 28 bits (host checks 2*S+2 <= 2^27)
 
 template <int D, bool FUSED>
 __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
@@ -80,6 +89,7 @@ __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
     float* __restrict__ attn_out, float* __restrict__ loc_out) {
   constexpr int G = D / 4;  // lanes per pair
   constexpr int PAIRS = 256 / G;
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ Level s_lvl[];
   load_levels(s_lvl, shapes, start, L);
   __syncthreads();
@@ -95,52 +105,52 @@ __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
   const int LP = L * P;
   const int64_t stride_px = (int64_t)M * D;
   const float* vb = value + (b * S * M + m) * (int64_t)D + sub * 4;
-  const float* lp = loc_or_off + pair * LP * 2;
+  const float2* lp = reinterpret_cast<const float2*>(loc_or_off) + pair * LP;
   const float* ap = attn_or_logit + pair * LP;
 
-  // FUSED: softmax statistics over the L*P logits of this pair (lanes of the group split the logits).
+  // FUSED: softmax statistics over the L*P logits of this pair; lane `sub` owns logits sub, sub+G, ...
   float smax = 0.f, ssum = 1.f;
-  const float* rp = nullptr;
+  const float2* rp = nullptr;
   if (FUSED) {
     float mx = -INFINITY;
-    for (int i = sub; i < LP; i += G) mx = fmaxf(mx, ld_stream(ap + i));
+    for (int i = sub; i < LP; i += G) mx = fmaxf(mx, __ldg(ap + i));
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, G));
+    for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o, G));
     float sum = 0.f;
     for (int i = sub; i < LP; i += G) sum += expf(__ldg(ap + i) - mx);
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, G);
+    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o, G);
     smax = mx;
     ssum = sum;
-    rp = ref + (int64_t)(q % Lr) * LP * 2;
+    rp = reinterpret_cast<const float2*>(ref) + (int64_t)(q % Lr) * LP;
   }
 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int l = 0; l < L; ++l) {
-    const Level lv = s_lvl[l];
-    const float* vl = vb + (int64_t)lv.start * stride_px;
-    const float fH = (float)lv.H, fW = (float)lv.W;
-#pragma unroll 2
-    for (int p = 0; p < P; ++p) {
+  int gl = 0, gp = 0;  // (level, point) of the sample the gather loop is at; advanced without divisions
+  for (int s0 = 0; s0 < LP; s0 += G) {
+    // ---- prep: this lane's sample ----
+    const int s = s0 + sub;
+    float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+    unsigned code = 0u;
+    if (s < LP) {
+      const Level lv = s_lvl[s / P];
+      const float fH = (float)lv.H, fW = (float)lv.W;
       float2 xy;
       float a;
       if (FUSED) {
-        const float2 off = __ldg(reinterpret_cast<const float2*>(lp));
-        const float2 r = __ldg(reinterpret_cast<const float2*>(rp));
+        const float2 off = ld_stream2(reinterpret_cast<const float*>(lp + s));
+        const float2 r = __ldg(rp + s);
         xy.x = r.x + off.x / fW;
         xy.y = r.y + off.y / fH;
-        a = expf(__ldg(ap) - smax) / ssum;
-        rp += 2;
-        if (sub == 0 && valid) {
-          if (attn_out) attn_out[pair * LP + l * P + p] = a;
-          if (loc_out) reinterpret_cast<float2*>(loc_out)[pair * LP + l * P + p] = xy;
+        a = expf(__ldg(ap + s) - smax) / ssum;
+        if (valid) {
+          if (attn_out) attn_out[pair * LP + s] = a;
+          if (loc_out) reinterpret_cast<float2*>(loc_out)[pair * LP + s] = xy;
         }
       } else {
-        xy = __ldg(reinterpret_cast<const float2*>(lp));
-        a = __ldg(ap);
+        xy = ld_stream2(reinterpret_cast<const float*>(lp + s));
+        a = ld_stream(ap + s);
       }
-      lp += 2;
-      ap += 1;
       // product rounded before the subtraction, as the reference's float*int - 0.5 (double) does (cuh:285-286)
       const float h_im = __fsub_rn(__fmul_rn(xy.y, fH), 0.5f);
       const float w_im = __fsub_rn(__fmul_rn(xy.x, fW), 0.5f);
@@ -148,18 +158,42 @@ __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
         const float hf = floorf(h_im), wf = floorf(w_im);
         const int h0 = (int)hf, w0 = (int)wf;
         const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-        const bool top = h0 >= 0, bot = h0 + 1 <= lv.H - 1, lef = w0 >= 0, rig = w0 + 1 <= lv.W - 1;
-        const float* p00 = vl + ((int64_t)h0 * lv.W + w0) * stride_px;
+        const unsigned top = h0 >= 0, bot = h0 + 1 <= lv.H - 1, lef = w0 >= 0, rig = w0 + 1 <= lv.W - 1;
+        const unsigned mask = (top & lef) | ((top & rig) << 1) | ((bot & lef) << 2) | ((bot & rig) << 3);
+        w1 = hh * hw * a;
+        w2 = hh * lw * a;
+        w3 = lh * hw * a;
+        w4 = lh * lw * a;
+        const int px = lv.start + h0 * lv.W + w0;  // >= -W-1
+        code = (unsigned)(px + kPxBias) | (mask << 28);
+      }
+    }
+    // ---- gather: the group's samples one by one ----
+    const int n = min(G, LP - s0);
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const unsigned cj = __shfl_sync(FULL, code, j, G);
+      const float a1 = __shfl_sync(FULL, w1, j, G);
+      const float a2 = __shfl_sync(FULL, w2, j, G);
+      const float a3 = __shfl_sync(FULL, w3, j, G);
+      const float a4 = __shfl_sync(FULL, w4, j, G);
+      if (cj >> 28) {
+        const int px = (int)(cj & 0x0fffffffu) - kPxBias;
+        const float* p00 = vb + (int64_t)px * stride_px;
+        const int W = s_lvl[gl].W;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 v1 = (top && lef) ? ldg4(p00) : z;
-        const float4 v2 = (top && rig) ? ldg4(p00 + stride_px) : z;
-        const float4 v3 = (bot && lef) ? ldg4(p00 + (int64_t)lv.W * stride_px) : z;
-        const float4 v4 = (bot && rig) ? ldg4(p00 + (int64_t)(lv.W + 1) * stride_px) : z;
-        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-        acc.x += (w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x) * a;
-        acc.y += (w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y) * a;
-        acc.z += (w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z) * a;
-        acc.w += (w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w) * a;
+        const float4 v1 = (cj & (1u << 28)) ? ldg4(p00) : z;
+        const float4 v2 = (cj & (2u << 28)) ? ldg4(p00 + stride_px) : z;
+        const float4 v3 = (cj & (4u << 28)) ? ldg4(p00 + (int64_t)W * stride_px) : z;
+        const float4 v4 = (cj & (8u << 28)) ? ldg4(p00 + (int64_t)(W + 1) * stride_px) : z;
+        acc.x += a1 * v1.x + a2 * v2.x + a3 * v3.x + a4 * v4.x;
+        acc.y += a1 * v1.y + a2 * v2.y + a3 * v3.y + a4 * v4.y;
+        acc.z += a1 * v1.z + a2 * v2.z + a3 * v3.z + a4 * v4.z;
+        acc.w += a1 * v1.w + a2 * v2.w + a3 * v3.w + a4 * v4.w;
+      }
+      if (++gp == P) {
+        gp = 0;
+        ++gl;
       }
     }
   }
@@ -216,7 +250,10 @@ static int dispatch_vec4(const float* value, const int64_t* shapes, const int64_
 #undef MVD_CASE
 }
 
-static bool vec4_ok(int D) { return D == 4 || D == 8 || D == 16 || D == 32 || D == 64 || D == 128; }
+static bool vec4_ok(int D, int S) {
+  if (2 * (int64_t)S + 2 > (int64_t)kPxBias) return false;  // packed pixel index of the vec4 kernels
+  return D == 4 || D == 8 || D == 16 || D == 32 || D == 64 || D == 128;
+}
 
 static int check_dims(int B, int S, int M, int D, int L, int Lq, int P) {
   if (B <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq <= 0 || P <= 0) return MVD_ERR_BAD_SHAPE;
@@ -234,7 +271,7 @@ extern "C" int mvd_msda_fwd_f32(const float* value, const int64_t* shapes, const
   if (!value || !shapes || !start || !loc || !attn || !out) return MVD_ERR_NULL_POINTER;
   if (int e = check_dims(B, S, M, D, L, Lq, P)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (vec4_ok(D) && aligned16(value) && aligned16(out) && aligned8(loc))
+  if (vec4_ok(D, S) && aligned16(value) && aligned16(out) && aligned8(loc))
     return dispatch_vec4<false>(value, shapes, start, loc, attn, nullptr, B, S, M, D, L, Lq, P, 1, out, nullptr,
                                 nullptr, st);
   return launch_scalar<float>(value, shapes, start, loc, attn, B, S, M, D, L, Lq, P, out, st);
@@ -255,7 +292,7 @@ extern "C" int mvd_msda_fused_fwd_f32(const float* value, const int64_t* shapes,
   if (!value || !shapes || !start || !offsets || !logits || !ref || !out) return MVD_ERR_NULL_POINTER;
   if (int e = check_dims(B, S, M, D, L, Lq, P)) return e;
   if (Lr <= 0) return MVD_ERR_BAD_SHAPE;
-  if (!vec4_ok(D)) return MVD_ERR_UNSUPPORTED;
+  if (!vec4_ok(D, S)) return MVD_ERR_UNSUPPORTED;
   if (!aligned16(value) || !aligned16(out) || !aligned8(offsets) || !aligned8(ref) ||
       (loc_out && !aligned8(loc_out)))
     return MVD_ERR_MISALIGNED;

@@ -105,10 +105,11 @@ __device__ __forceinline__ Taps make_taps(const float* T, int u, int v, int Hi, 
   return t;
 }
 
-template <int CCH, bool CHANNELS_LAST>
-__global__ void __launch_bounds__(kWarpThreads) warp_fwd_kernel(const float* __restrict__ src,
-                                                                const float* __restrict__ Mat, int C, int Hi, int Wi,
-                                                                int Ho, int Wo, float* __restrict__ dst) {
+// NCHW destination: x = destination pixel, y = chunk of CCH channels, z = view.
+template <int CCH>
+__global__ void __launch_bounds__(kWarpThreads) warp_fwd_nchw_kernel(const float* __restrict__ src,
+                                                                     const float* __restrict__ Mat, int C, int Hi,
+                                                                     int Wi, int Ho, int Wo, float* __restrict__ dst) {
   __shared__ float sT[9];
   const int n = blockIdx.z;
   if (threadIdx.x == 0) normalized_inverse(Mat + 9 * n, Hi, Wi, Ho, Wo, sT);
@@ -119,50 +120,78 @@ __global__ void __launch_bounds__(kWarpThreads) warp_fwd_kernel(const float* __r
   const int v = pix / Wo, u = pix - v * Wo;
   const Taps t = make_taps(sT, u, v, Hi, Wi, Ho, Wo);
   const int c0 = blockIdx.y * CCH;
-  const int64_t plane = (int64_t)Hi * Wi;
+  const int64_t plane = (int64_t)Hi * Wi, oplane = (int64_t)Ho * Wo;
   const float* sp = src + ((int64_t)n * C + c0) * plane + t.o00;
+  float* dp = dst + ((int64_t)n * C + c0) * oplane + pix;
   const bool any = t.m_nw || t.m_ne || t.m_sw || t.m_se;
-
-  if (CHANNELS_LAST) {
-    float* dp = dst + ((int64_t)n * Ho * Wo + pix) * C + c0;
-#pragma unroll
-    for (int cc = 0; cc < CCH; cc += 4) {
-      float r[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float acc = 0.f;
-        if (any && c0 + cc + j < C) {
-          const float* s = sp + (int64_t)(cc + j) * plane;
-          if (t.m_nw) acc += __ldg(s) * t.nw;
-          if (t.m_ne) acc += __ldg(s + 1) * t.ne;
-          if (t.m_sw) acc += __ldg(s + Wi) * t.sw;
-          if (t.m_se) acc += __ldg(s + Wi + 1) * t.se;
-        }
-        r[j] = acc;
-      }
-      if (c0 + cc + 3 < C && (C & 3) == 0) {
-        *reinterpret_cast<float4*>(dp + cc) = make_float4(r[0], r[1], r[2], r[3]);
-      } else {
-        for (int j = 0; j < 4; ++j)
-          if (c0 + cc + j < C) dp[cc + j] = r[j];
-      }
-    }
-  } else {
-    const int64_t oplane = (int64_t)Ho * Wo;
-    float* dp = dst + ((int64_t)n * C + c0) * oplane + pix;
 #pragma unroll 8
-    for (int cc = 0; cc < CCH; ++cc) {
-      if (c0 + cc >= C) break;
+  for (int cc = 0; cc < CCH; ++cc) {
+    if (c0 + cc >= C) break;
+    float acc = 0.f;
+    if (any) {
+      const float* s = sp + (int64_t)cc * plane;
+      if (t.m_nw) acc += __ldg(s) * t.nw;
+      if (t.m_ne) acc += __ldg(s + 1) * t.ne;
+      if (t.m_sw) acc += __ldg(s + Wi) * t.sw;
+      if (t.m_se) acc += __ldg(s + Wi + 1) * t.se;
+    }
+    __stcs(dp + (int64_t)cc * oplane, acc);  // streaming store: written once, read by the next layer
+  }
+}
+
+// Channels-last destination [BN, Ho, Wo, C]: a block owns 32 consecutive destination pixels of one view.
+//   gather : lane = pixel (neighbouring pixels read neighbouring source texels of the same plane), the 4 warps
+//            stride the channels; results go to a [channel][pixel] shared tile (pitch 33: conflict-free);
+//   store  : each warp emits whole pixel rows, lane = channel, i.e. 128-byte fully coalesced stores.
+constexpr int kTilePx = 32, kTileCh = 128, kTilePitch = 33;
+
+__global__ void __launch_bounds__(kWarpThreads) warp_fwd_nhwc_kernel(const float* __restrict__ src,
+                                                                     const float* __restrict__ Mat, int C, int Hi,
+                                                                     int Wi, int Ho, int Wo, float* __restrict__ dst) {
+  __shared__ float sT[9];
+  __shared__ float tile[kTileCh * kTilePitch];
+  const int n = blockIdx.y;
+  if (threadIdx.x == 0) normalized_inverse(Mat + 9 * n, Hi, Wi, Ho, Wo, sT);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npix = Ho * Wo;
+  const int pix0 = blockIdx.x * kTilePx;
+  const int pix = pix0 + lane;
+  const bool in = pix < npix;
+  const int v = in ? pix / Wo : 0, u = in ? pix - v * Wo : 0;
+  Taps t = make_taps(sT, u, v, Hi, Wi, Ho, Wo);
+  const bool any = in && (t.m_nw || t.m_ne || t.m_sw || t.m_se);
+  const int64_t plane = (int64_t)Hi * Wi;
+  const float* sp = src + (int64_t)n * C * plane + t.o00;
+  const int rows = min(kTilePx, npix - pix0);
+
+  for (int c0 = 0; c0 < C; c0 += kTileCh) {
+    const int nch = min(kTileCh, C - c0);
+#pragma unroll 8
+    for (int i = 0; i < kTileCh / 4; ++i) {
+      const int c = warp + 4 * i;
+      if (c >= nch) break;
       float acc = 0.f;
       if (any) {
-        const float* s = sp + (int64_t)cc * plane;
+        const float* s = sp + (int64_t)(c0 + c) * plane;
         if (t.m_nw) acc += __ldg(s) * t.nw;
         if (t.m_ne) acc += __ldg(s + 1) * t.ne;
         if (t.m_sw) acc += __ldg(s + Wi) * t.sw;
         if (t.m_se) acc += __ldg(s + Wi + 1) * t.se;
       }
-      __stcs(dp + (int64_t)cc * oplane, acc);  // streaming store: written once, read by the next layer
+      tile[c * kTilePitch + lane] = acc;
     }
+    __syncthreads();
+    for (int r = warp; r < rows; r += 4) {
+      float* dp = dst + ((int64_t)n * npix + pix0 + r) * C + c0;
+#pragma unroll
+      for (int k = 0; k < kTileCh / 32; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nch) __stcs(dp + c, tile[c * kTilePitch + r]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -211,15 +240,15 @@ extern "C" int mvd_warp_fwd_f32(const float* src, const float* Mat, int BN, int 
                                 float* dst, int channels_last, void* stream) {
   if (!src || !Mat || !dst) return MVD_ERR_NULL_POINTER;
   if (int e = check_warp_dims(BN, C, Hi, Wi, Ho, Wo)) return e;
-  constexpr int CCH = 16;
-  dim3 grid((unsigned)ceil_div64((int64_t)Ho * Wo, kWarpThreads), (unsigned)ceil_div64(C, CCH), (unsigned)BN);
-  if (grid.y > 65535) return MVD_ERR_BAD_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   if (channels_last) {
-    if ((reinterpret_cast<uintptr_t>(dst) & 15u) != 0) return MVD_ERR_MISALIGNED;
-    warp_fwd_kernel<CCH, true><<<grid, kWarpThreads, 0, st>>>(src, Mat, C, Hi, Wi, Ho, Wo, dst);
+    dim3 grid((unsigned)ceil_div64((int64_t)Ho * Wo, kTilePx), (unsigned)BN);
+    warp_fwd_nhwc_kernel<<<grid, kWarpThreads, 0, st>>>(src, Mat, C, Hi, Wi, Ho, Wo, dst);
   } else {
-    warp_fwd_kernel<CCH, false><<<grid, kWarpThreads, 0, st>>>(src, Mat, C, Hi, Wi, Ho, Wo, dst);
+    constexpr int CCH = 16;
+    dim3 grid((unsigned)ceil_div64((int64_t)Ho * Wo, kWarpThreads), (unsigned)ceil_div64(C, CCH), (unsigned)BN);
+    if (grid.y > 65535) return MVD_ERR_BAD_SHAPE;
+    warp_fwd_nchw_kernel<CCH><<<grid, kWarpThreads, 0, st>>>(src, Mat, C, Hi, Wi, Ho, Wo, dst);
   }
   MVD_LAUNCH_CHECK();
   return MVD_OK;

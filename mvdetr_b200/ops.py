@@ -212,6 +212,24 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     return (out, attn, loc) if want_aux else out
 
 
+def add_layer_norm(x, res, weight, bias, eps=1e-5):
+    """LayerNorm(x + res) over the last dim in one kernel (inference glue of the encoder layer,
+    ref: multiview_detector/models/deformable_transformer.py:79-80,84-85). res may be None."""
+    C = x.shape[-1]
+    for name, t in (("x", x), ("res", res), ("weight", weight), ("bias", bias)):
+        if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError(f"add_layer_norm: {name} must be a contiguous fp32 CUDA tensor")
+    if res is not None and res.shape != x.shape:
+        raise RuntimeError("add_layer_norm: x and res must have the same shape")
+    out = torch.empty_like(x)
+    with _on_device(x):
+        rc = _C.lib.mvd_add_layernorm_f32(x.data_ptr(), res.data_ptr() if res is not None else None,
+                                          weight.data_ptr(), bias.data_ptr(), x.numel() // C, C, float(eps),
+                                          out.data_ptr(), _stream(x))
+    _C.check(rc, "mvd_add_layernorm_f32")
+    return out
+
+
 class _WarpPerspective(Function):
     @staticmethod
     def forward(ctx, src, mat, Ho, Wo, channels_last):

@@ -156,6 +156,14 @@ class DeformableTransformerEncoderLayer(nn.Module):
                 geometry=None, ref_table=None):
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                               level_start_index, padding_mask, geometry=geometry, ref_table=ref_table)
+        if (not torch.is_grad_enabled() and not self.training and src.is_cuda and src.dtype == torch.float32
+                and src.shape[-1] % 4 == 0 and src.shape[-1] <= 1024):
+            # inference: residual+LayerNorm in one kernel, bias+ReLU in the GEMM epilogue; same arithmetic
+            src = ops.add_layer_norm(src.contiguous(), src2.contiguous(), self.norm1.weight, self.norm1.bias,
+                                     self.norm1.eps)
+            hidden = torch._addmm_activation(self.linear1.bias, src.view(-1, src.shape[-1]), self.linear1.weight.t())
+            src2 = self.linear2(hidden).view(src.shape)
+            return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps)
         src = self.norm1(src + self.dropout1(src2))
         src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
         return self.norm2(src + self.dropout3(src2))

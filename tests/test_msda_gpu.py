@@ -43,12 +43,27 @@ def test_golden_forward_backward(golden, cuda, name, dtype):
     else:
         tol = dict(rtol=0, atol=FP32_ATOL)
     assert np.allclose(out.detach().cpu().numpy(), g["out"], **tol)
-    # gradients are sums of up to Lq*M*L*P*4 atomics per element; fp32 tolerance scales with their magnitude
-    for got, key in ((value.grad, "grad_value"), (loc.grad, "grad_loc"), (attn.grad, "grad_attn")):
+    # grad_loc is piecewise constant in the sampling position: a sample within fp32 rounding of a cell boundary
+    # (msda_mvdetr_mini has one at w_im = 3 - 6e-8) lands in the neighbouring cell in fp32. Mask those samples when
+    # comparing fp32 results with the fp64 golden; the same-precision C oracle is compared unmasked.
+    shp = g["shapes"].astype(np.float64)
+    px = g["loc"] * shp[None, None, None, :, None, ::-1] - 0.5
+    near = (np.abs(px - np.round(px)) < 1e-4).any(-1)
+    n32 = [g[k].astype(np.float32) for k in ("grad_out", "value", "loc", "attn")]
+    same_prec = co.msda_backward(n32[0], n32[1], g["shapes"], g["start"], n32[2], n32[3])
+    for got, key, sp in zip((value.grad, loc.grad, attn.grad), ("grad_value", "grad_loc", "grad_attn"), same_prec):
         ref = g[key]
         scale = max(1.0, float(np.abs(ref).max()))
-        err = np.abs(got.cpu().numpy() - ref).max()
-        assert err <= (1e-9 if dtype == torch.float64 else FP32_ATOL) * scale, (key, err)
+        got = got.cpu().numpy()
+        if dtype == torch.float64:
+            assert np.abs(got - ref).max() <= 1e-9 * scale, key
+            continue
+        assert np.abs(got - sp).max() <= FP32_ATOL * scale, (key, "vs fp32 C oracle")
+        err = np.abs(got - ref)
+        if key == "grad_loc":
+            err = err[~near]
+        if key != "grad_value" or not near.any():  # grad_value scatter targets also move with the cell
+            assert err.max() <= FP32_ATOL * scale, (key, err.max())
 
 
 @pytest.mark.parametrize("D", [16, 30, 32, 64, 71, 1025, 2048, 3096])
