@@ -1,0 +1,227 @@
+"""View-sharded multi-GPU execution of the fusion stage: one process per GPU, camera views split across ranks.
+
+What shards: backbone features, the perspective warp and the stride-2 downsample conv are independent per
+view (the reference folds views into the batch dim: multiview_detector/models/mvdetr.py:153,177-178,194;
+trans_world_feat.py:89), and so are the encoder's per-token Linear / LayerNorm / FFN. Views couple only through the
+deformable attention's `value` (every query samples all L = num_cam levels). Hence, per frame, on rank r owning the
+contiguous view range [v0, v1):
+
+    warp(views v0..v1) -> downsample conv -> tokens src_r [(v1-v0)*Hd*Wd, C]
+    for each of the 3 encoder layers:
+        value_r = value_proj(src_r)                       (local rows only)
+        value   = ALL-GATHER(value_r)   <-- the one exchange step per layer (5.5 MB / view at Wildtrack size)
+        src_r   = layer(src_r, queries of the local views sampling the full `value`)
+    memory = ALL-GATHER(src_r)                            (for the merge conv over all views)
+    rank-replicated merge_linear + upsample (identical on every rank; rank 0's copy is the result)
+
+The first all-gather is the north star's "all-gather of warped world-grid features before the transformer" (the
+warped features, after the per-view conv and the per-token value projection, both of which commute with the gather).
+Results equal the single-GPU path up to the reduction order inside cuBLAS (row partitions of the same GEMMs).
+
+Views do not have to divide the world size: ranks take ceil(N/world) views each, trailing ranks may own fewer or
+none; gather buffers are padded to the maximum and the valid rows form a contiguous prefix (no compaction copy).
+
+`gather_rows` runs on any torch.distributed backend (NCCL on the GPUs; gloo in the CPU tests of the host logic).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class ViewPartition:
+    """Contiguous split of `num_views` over `world` ranks: rank r owns views [lo(r), hi(r))."""
+
+    def __init__(self, num_views, world):
+        if num_views <= 0 or world <= 0:
+            raise ValueError("num_views and world must be positive")
+        self.num_views, self.world = int(num_views), int(world)
+        self.per_rank = -(-self.num_views // self.world)  # ceil
+
+    def lo(self, rank):
+        return min(self.num_views, rank * self.per_rank)
+
+    def hi(self, rank):
+        return min(self.num_views, (rank + 1) * self.per_rank)
+
+    def count(self, rank):
+        return self.hi(rank) - self.lo(rank)
+
+    def active_ranks(self):
+        return [r for r in range(self.world) if self.count(r) > 0]
+
+
+def gather_rows(local_rows, partition, rows_per_view, rank, out=None, group=None):
+    """All-gather of per-view row blocks. local_rows [count(rank)*rows_per_view, C] -> [num_views*rows_per_view, C]
+    (a view of the padded gather buffer `out` [world, per_rank*rows_per_view, C], allocated when None)."""
+    C = local_rows.shape[-1]
+    pad_rows = partition.per_rank * rows_per_view
+    if out is None:
+        out = local_rows.new_empty((partition.world, pad_rows, C))
+    mine = out[rank]
+    n = local_rows.shape[0]
+    if mine.data_ptr() != local_rows.data_ptr():
+        mine[:n].copy_(local_rows)
+    if partition.world > 1:
+        dist.all_gather_into_tensor(out.view(-1), mine.reshape(-1), group=group)
+    return out.view(partition.world * pad_rows, C)[:partition.num_views * rows_per_view]
+
+
+class ShardedFusion:
+    """Inference-only view-sharded forward over a MultiviewFusion's parameters (every rank holds the full, identical
+    parameter set; only activations are sharded)."""
+
+    def __init__(self, fusion, rank, world, group=None):
+        self.fusion = fusion
+        self.wf = fusion.world_feat
+        self.rank, self.world, self.group = rank, world, group
+        self.part = ViewPartition(fusion.num_cam, world)
+        self.v0, self.v1 = self.part.lo(rank), self.part.hi(rank)
+        self._bufs = {}
+
+    def _buf(self, key, shape, like):
+        b = self._bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape) or b.device != like.device:
+            b = self._bufs[key] = torch.zeros(shape, dtype=like.dtype, device=like.device)
+        return b
+
+    def tokens(self, feat_local, proj_local):
+        """warp + downsample of the local views -> [nv*Hd*Wd, C] token rows (and Hd, Wd)."""
+        wf = self.wf
+        Hg, Wg = self.fusion.Rworld_shape
+        nv = feat_local.shape[0]
+        C = wf.hidden_dim
+        if nv == 0:
+            Hd, Wd = wf.pos_embedding.shape[-2:]
+            return feat_local.new_zeros((0, C)), Hd, Wd
+        world = ops.warp_perspective(feat_local, proj_local, (Hg, Wg), align_corners=False, channels_last=True)
+        x = wf.downsample(world.permute(0, 3, 1, 2))
+        Hd, Wd = x.shape[-2:]
+        return x.permute(0, 2, 3, 1).reshape(nv * Hd * Wd, C), Hd, Wd
+
+    def encode(self, src_local, Hd, Wd, slot=0):
+        """Query-sharded encoder + replicated merge/upsample. src_local [nv*Hd*Wd, C] -> [1, hidden, Hg, Wg]."""
+        wf, part, rank = self.wf, self.part, self.rank
+        N, C, hw = self.fusion.num_cam, wf.hidden_dim, Hd * Wd
+        S = N * hw
+        dev = src_local.device
+        geo = wf._level_geometry(N, Hd, Wd, dev)
+        table = wf.encoder.ref_table
+        if table is None:
+            raise RuntimeError("ShardedFusion needs the compact reference table (MVDeTr's create_reference_map layout)")
+        nq = src_local.shape[0]
+        q0 = self.v0 * hw
+        pos = (wf.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) + wf.lvl_embedding.view(1, N, 1, C)
+               ).view(S, C)[q0:q0 + nq]
+        gbuf = self._buf(("gather", slot), (part.world, part.per_rank * hw, C), src_local)
+        src = src_local
+        for layer in wf.encoder.layers:
+            attn = layer.self_attn
+            M, L, P = attn.n_heads, attn.n_levels, attn.n_points
+            mine = gbuf[rank][:nq]
+            if nq:
+                torch.addmm(attn.value_proj.bias, src, attn.value_proj.weight.t(), out=mine)  # local rows in place
+            value = gather_rows(mine, part, hw, rank, out=gbuf, group=self.group)
+            if nq:
+                query = src + pos
+                offsets = attn.sampling_offsets(query).view(1, nq, M, L, P, 2)
+                logits = attn.attention_weights(query).view(1, nq, M, L * P)
+                out = ops.msda_fused_forward(value.view(1, S, M, C // M), geo.shapes, geo.start, offsets, logits,
+                                             table)
+                src2 = attn.output_proj(out.view(nq, C))
+                src = ops.add_layer_norm(src, src2, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+                hidden = torch._addmm_activation(layer.linear1.bias, src, layer.linear1.weight.t())
+                src2 = layer.linear2(hidden)
+                src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+        memory = gather_rows(src, part, hw, rank, out=gbuf, group=self.group)
+        merged = wf.merge_linear(memory.view(1, N, Hd, Wd, C).permute(0, 1, 4, 2, 3).reshape(1, N * C, Hd, Wd))
+        return wf.upsample(merged)
+
+    def fuse(self, feat_local, proj_local, slot=0):
+        src, Hd, Wd = self.tokens(feat_local, proj_local)
+        return self.encode(src, Hd, Wd, slot)
+
+
+class ShardedFrameRunner:
+    """FrameRunner's interface (load / step / run_host_frames) for the view-sharded path. `load` and
+    `run_host_frames` take FULL frames and keep this rank's views only; the fused world feature is valid on every rank
+    (rank 0's copy is the one the bench reads back)."""
+
+    frames_per_step = 1
+
+    def __init__(self, fusion, feat_shape, device, rank, world, use_graph=True, depth=2, group=None):
+        self.device = torch.device(device)
+        self.fusion = fusion.to(device).eval()
+        self.sf = ShardedFusion(self.fusion, rank, world, group)
+        self.rank, self.world, self.depth = rank, world, depth
+        self.mode = f"views{fusion.num_cam}_over_{world}ranks_allgather"
+        v0, v1 = self.sf.v0, self.sf.v1
+        self.feat = [torch.zeros((v1 - v0, *feat_shape[1:]), device=device) for _ in range(depth)]
+        self.proj = [torch.eye(3, device=device).repeat(v1 - v0, 1, 1) for _ in range(depth)]
+        self.out = [None] * depth
+        self.graphs = [None] * depth
+        self.compute = torch.cuda.Stream(device=device)
+        self.s_in = torch.cuda.Stream(device=device)
+        self.s_out = torch.cuda.Stream(device=device)
+        with torch.no_grad(), torch.cuda.stream(self.compute):
+            for i in range(depth):
+                for _ in range(2):
+                    self.out[i] = self.sf.fuse(self.feat[i], self.proj[i], slot=i)
+            self.compute.synchronize()
+            if use_graph:
+                try:
+                    for i in range(depth):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=self.compute):
+                            self.out[i] = self.sf.fuse(self.feat[i], self.proj[i], slot=i)
+                        self.graphs[i] = g
+                except Exception as e:  # NCCL capture unsupported on this stack: stay eager, say so
+                    self.graphs = [None] * depth
+                    self.mode += f"_eager({type(e).__name__})"
+                    torch.cuda.synchronize(device)
+        torch.cuda.synchronize(device)
+
+    def load(self, imgs_feat, proj_mats, slot=0):
+        v0, v1 = self.sf.v0, self.sf.v1
+        self.feat[slot].copy_(imgs_feat[v0:v1])
+        self.proj[slot].copy_(proj_mats[v0:v1])
+
+    def step(self, slot=0):
+        with torch.cuda.stream(self.compute):
+            if self.graphs[slot] is not None:
+                self.graphs[slot].replay()
+            else:
+                with torch.no_grad():
+                    self.out[slot] = self.sf.fuse(self.feat[slot], self.proj[slot], slot=slot)
+        return self.out[slot]
+
+    def run_host_frames(self, feats_pinned, Ms, outs_pinned):
+        """Same pipeline as FrameRunner.run_host_frames; each rank uploads only its own views (in deployment every
+        GPU's host process receives its own cameras) and rank 0 reads the fused result back."""
+        v0, v1 = self.sf.v0, self.sf.v1
+        n = len(feats_pinned)
+        ev_in = [torch.cuda.Event() for _ in range(self.depth)]
+        ev_done = [torch.cuda.Event() for _ in range(self.depth)]
+        ev_out = [torch.cuda.Event() for _ in range(self.depth)]
+        for i in range(n):
+            s = i % self.depth
+            proj = self.fusion.projection(Ms[i])[v0:v1]
+            with torch.cuda.stream(self.s_in):
+                if i >= self.depth:
+                    self.s_in.wait_event(ev_done[s])
+                if v1 > v0:
+                    self.feat[s].copy_(feats_pinned[i][v0:v1], non_blocking=True)
+                    self.proj[s].copy_(proj, non_blocking=True)
+                ev_in[s].record(self.s_in)
+            self.compute.wait_event(ev_in[s])
+            if i >= self.depth:
+                self.compute.wait_event(ev_out[s])
+            self.step(s)
+            ev_done[s].record(self.compute)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_done[s])
+                if self.rank == 0:
+                    outs_pinned[i].copy_(self.out[s], non_blocking=True)
+                ev_out[s].record(self.s_out)
+        self.s_out.synchronize()
+        self.compute.synchronize()
