@@ -102,12 +102,21 @@ MVD_API int mvd_msda_bwd_f64(const double* grad_out, const double* value, const 
  * in shared memory with TMA. Sampling locations are still arbitrary: samples that fall outside the
  * staged window take a global-memory path, so the hint can only change speed, never results.
  *   value [B, L*H*W, M, D], loc [B, R*H*W, M, L, P, 2], attn [B, R*H*W, M, L, P], out [B, R*H*W, M*D]
- * Returns MVD_ERR_UNSUPPORTED when (D, P, ...) has no tiled instantiation; callers then use
- * mvd_msda_fwd_f32.
+ * Returns MVD_ERR_UNSUPPORTED when (D, P, R) has no tiled instantiation (D in {8,16,32}, P in {4,8}); callers then
+ * use mvd_msda_fwd_f32. MVD_ERR_NO_DEVICE when the driver's cuTensorMapEncodeTiled cannot be resolved.
  * ------------------------------------------------------------------------------------------ */
 MVD_API int mvd_msda_fwd_viewgrid_f32(const float* value, const float* loc, const float* attn,
                               int B, int H, int W, int M, int D, int L, int R, int P,
                               float* out, void* stream);
+
+/* View-grid variant of mvd_msda_fused_fwd_f32 below (grid given as host ints; S = L*H*W, Lq = R*H*W).
+ * `ref_lm` is the reference table in LEVEL-MAJOR order [L, Lr, P, 2] (query q reads row q % Lr of every level),
+ * which lets neighbouring ground cells read neighbouring 32-byte sectors. loc/ref pointers 32-byte aligned. The softmax is evaluated online (running max, one division at the
+ * end), so results agree with mvd_msda_fused_fwd_f32 to rounding; attn_out / loc_out must be NULL here
+ * (MVD_ERR_UNSUPPORTED otherwise: callers that need them use mvd_msda_fused_fwd_f32). */
+MVD_API int mvd_msda_fused_fwd_viewgrid_f32(const float* value, const float* offsets, const float* logits,
+                                    const float* ref_lm, int B, int H, int W, int M, int D, int L, int R, int P, int Lr,
+                                    float* out, float* attn_out, float* loc_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused sampling-location + softmax + deformable attention, forward ("next" row).

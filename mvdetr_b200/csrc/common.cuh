@@ -69,6 +69,17 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
                : "l"(p));
   return v;
 }
+// 256-bit global load (sm_100+): one request per lane for a whole 32-byte sector. p must be 32-byte aligned.
+__device__ __forceinline__ void ld_stream8(const float* p, float* v) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg8(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)

@@ -187,11 +187,15 @@ def msda_viewgrid_forward(value, sampling_loc, attn_weight, H, W):
     return out
 
 
-def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits, ref_table, want_aux=False):
+def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits, ref_table, want_aux=False,
+                       grid_hw=None, ref_table_lm=None):
     """out = MSDA(value, loc = ref + offsets/(W_l,H_l), attn = softmax(logits)) in one kernel (inference path).
 
     value [B,S,M,D] fp32; offsets [B,Lq,M,L,P,2] and logits [B,Lq,M,L*P]: raw Linear outputs; ref_table [Lr,L,P,2]
-    (query q reads row q % Lr). Returns out [B,Lq,M*D], plus (attn, loc) when want_aux."""
+    (query q reads row q % Lr). Returns out [B,Lq,M*D], plus (attn, loc) when want_aux.
+    grid_hw=(H, W) (host ints) asserts the MVDeTr encoder layout -- every level an HxW grid, S = L*H*W, Lq = R*H*W --
+    and selects the TMA-staged view-grid kernel; the generic kernel is used when that layout has no instantiation.
+    ref_table_lm: optional precomputed level-major copy of ref_table, [L,Lr,P,2] (made on the fly when None)."""
     B, S, M, D = value.shape
     _, Lq, _, L, P, _ = offsets.shape
     for name, t in (("value", value), ("offsets", offsets), ("logits", logits), ("ref_table", ref_table)):
@@ -202,12 +206,27 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
     attn = torch.empty((B, Lq, M, L, P), dtype=value.dtype, device=value.device) if want_aux else None
     loc = torch.empty_like(offsets) if want_aux else None
+    aux = (attn.data_ptr() if want_aux else None, loc.data_ptr() if want_aux else None)
     with _on_device(value):
+        if grid_hw is not None and _VIEWGRID and not want_aux:
+            H, W = int(grid_hw[0]), int(grid_hw[1])
+            if S != L * H * W or Lq % (H * W) != 0:
+                raise RuntimeError("msda_fused_forward: grid_hw does not match value/queries")
+            if ref_table_lm is None:
+                ref_table_lm = ref_table.permute(1, 0, 2, 3).contiguous()
+            elif tuple(ref_table_lm.shape) != (L, ref_table.shape[0], P, 2) or not ref_table_lm.is_contiguous():
+                raise RuntimeError("msda_fused_forward: ref_table_lm must be contiguous [L, Lr, P, 2]")
+            rc = _C.lib.mvd_msda_fused_fwd_viewgrid_f32(value.data_ptr(), offsets.data_ptr(), logits.data_ptr(),
+                                                        ref_table_lm.data_ptr(), B, H, W, M, D, L, Lq // (H * W), P,
+                                                        ref_table.shape[0], out.data_ptr(), None, None,
+                                                        _stream(value))
+            if rc == 0:
+                return (out, attn, loc) if want_aux else out
+            if rc != -3:  # MVD_ERR_UNSUPPORTED -> generic kernel
+                _C.check(rc, "mvd_msda_fused_fwd_viewgrid_f32")
         rc = _C.lib.mvd_msda_fused_fwd_f32(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                                            offsets.data_ptr(), logits.data_ptr(), ref_table.data_ptr(), B, S, M, D, L,
-                                           Lq, P, ref_table.shape[0], out.data_ptr(),
-                                           attn.data_ptr() if want_aux else None,
-                                           loc.data_ptr() if want_aux else None, _stream(value))
+                                           Lq, P, ref_table.shape[0], out.data_ptr(), *aux, _stream(value))
     _C.check(rc, "mvd_msda_fused_fwd_f32")
     return (out, attn, loc) if want_aux else out
 

@@ -127,7 +127,7 @@ class ShardedFusion:
                 offsets = attn.sampling_offsets(query).view(1, nq, M, L, P, 2)
                 logits = attn.attention_weights(query).view(1, nq, M, L * P)
                 out = ops.msda_fused_forward(value.view(1, S, M, C // M), geo.shapes, geo.start, offsets, logits,
-                                             table)
+                                             table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm)
                 src2 = attn.output_proj(out.view(nq, C))
                 src = ops.add_layer_norm(src, src2, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
                 hidden = torch._addmm_activation(layer.linear1.bias, src, layer.linear1.weight.t())

@@ -95,7 +95,7 @@ class MSDeformAttn(nn.Module):
         constant_(self.output_proj.bias.data, 0.)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, geometry=None, ref_table=None):
+                input_padding_mask=None, geometry=None, ref_table=None, ref_table_lm=None):
         """Reference signature (first six arguments). Extensions used by our encoder: `geometry` (LevelGeometry,
         avoids the device->host check) and `ref_table` ([Lr,L,P,2] compact reference points: enables the fused
         kernel when autograd is off)."""
@@ -117,8 +117,10 @@ class MSDeformAttn(nn.Module):
         fused = (ref_table is not None and not torch.is_grad_enabled() and value.dtype == torch.float32 and
                  value.is_cuda)
         if fused:
+            grid_hw = geometry.hw[0] if geometry is not None and geometry.uniform else None
             output = ops.msda_fused_forward(value.contiguous(), input_spatial_shapes, input_level_start_index,
-                                            sampling_offsets.contiguous(), attention_weights.contiguous(), ref_table)
+                                            sampling_offsets.contiguous(), attention_weights.contiguous(), ref_table,
+                                            grid_hw=grid_hw, ref_table_lm=ref_table_lm)
             return self.output_proj(output)
 
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
@@ -153,9 +155,10 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
-                geometry=None, ref_table=None):
+                geometry=None, ref_table=None, ref_table_lm=None):
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
-                              level_start_index, padding_mask, geometry=geometry, ref_table=ref_table)
+                              level_start_index, padding_mask, geometry=geometry, ref_table=ref_table,
+                              ref_table_lm=ref_table_lm)
         if (not torch.is_grad_enabled() and not self.training and src.is_cuda and src.dtype == torch.float32
                 and src.shape[-1] % 4 == 0 and src.shape[-1] <= 1024):
             # inference: residual+LayerNorm in one kernel, bias+ReLU in the GEMM epilogue; same arithmetic
@@ -177,6 +180,7 @@ class DeformableTransformerEncoder(nn.Module):
         # reference keeps this as a plain CPU attribute and uploads it every call (deformable_transformer.py:27,48)
         self.register_buffer("reference_points", reference_points, persistent=False)
         self.register_buffer("ref_table", None, persistent=False)
+        self.register_buffer("ref_table_lm", None, persistent=False)  # level-major copy [L, rows, P, 2]
 
     def set_compact_table(self, rows):
         """If reference_points is `k` identical copies of its first `rows` rows (MVDeTr: mvdetr.py:130), keep the
@@ -188,6 +192,7 @@ class DeformableTransformerEncoder(nn.Module):
                                                                                            -1, -1)):
             return False
         self.ref_table = rp[:rows].contiguous().float()
+        self.ref_table_lm = self.ref_table.permute(1, 0, 2, 3).contiguous()
         return True
 
     @staticmethod
@@ -213,7 +218,7 @@ class DeformableTransformerEncoder(nn.Module):
             reference_points = self.reference_points.unsqueeze(0).expand(src.shape[0], -1, -1, -1, -1)
         for layer in self.layers:
             output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
-                           geometry=geometry, ref_table=self.ref_table)
+                           geometry=geometry, ref_table=self.ref_table, ref_table_lm=self.ref_table_lm)
         return output
 
 

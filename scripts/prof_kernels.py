@@ -42,6 +42,7 @@ def main():
         table = wf.encoder.ref_table
         out, attn, loc = ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table, want_aux=True)
         ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table)
+        ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm)
         ops.ms_deform_attn_forward(value, geo.shapes, geo.start, loc, attn, 64)
         ops.ms_deform_attn_backward(value, geo.shapes, geo.start, loc, attn, torch.randn_like(out), 64)
         gw = torch.randn_like(world)

@@ -217,3 +217,53 @@ def test_host_buffer_entry_point(cuda):
     assert rc == 0, _C.error_string(rc)
     out_dev = run_fwd(*(t.to(cuda) for t in prob[:5]))
     assert torch.equal(out_host, out_dev.cpu())
+
+
+@pytest.mark.parametrize("L,H,W,M,D,P,R,B,offset_px", [
+    (7, 30, 45, 8, 16, 4, 7, 1, 3.0),     # MVDeTr layout, offsets inside the staged window
+    (7, 30, 45, 8, 16, 4, 7, 1, 40.0),    # most samples leave the window -> masked global path, same results
+    (3, 13, 21, 2, 16, 4, 5, 2, 8.0),     # partial tiles, R != L, batch 2, mixed window/global
+    (6, 9, 50, 4, 32, 8, 6, 1, 5.0),      # D=32, P=8 instantiation
+    (2, 5, 7, 3, 8, 4, 1, 1, 2.0),        # D=8, a single replica of a grid smaller than one tile
+    (4, 17, 33, 2, 16, 8, 20, 1, 6.0),    # many replicas -> smaller tile
+])
+def test_viewgrid_kernel_vs_c_oracle(cuda, L, H, W, M, D, P, R, B, offset_px):
+    """The TMA-staged view-grid kernel (host-int geometry) against the C oracle and bit-level against nothing less:
+    window path, out-of-window fallback, zero-filled borders, partial tiles."""
+    probs = [viewgrid_problem(L, H, W, M, D, P, seed=50 + b, R=R, offset_px=offset_px) for b in range(B)]
+    value, loc, attn = (torch.cat([p[i] for p in probs]).to(cuda) for i in (0, 3, 4))
+    shapes, start = probs[0][1], probs[0][2]
+    out = ops.msda_viewgrid_forward(value, loc, attn, H, W)
+    ref = co.msda_forward(value.cpu().numpy(), shapes.numpy(), start.numpy(), loc.cpu().numpy(), attn.cpu().numpy())
+    assert np.abs(out.cpu().numpy() - ref).max() <= FP32_ATOL
+    # the drop-in op picks the same kernel from the device-side shapes and must agree exactly
+    via_op = ops.ms_deform_attn_forward(value, shapes.to(cuda), start.to(cuda), loc, attn, 64)
+    assert torch.equal(via_op, out)
+
+
+def test_viewgrid_fused_matches_unfused_and_generic(cuda):
+    """Fused (offsets/logits/ref-table) view-grid kernel == generic fused kernel's aux outputs fed to the plain op."""
+    L, H, W, M, D, P = 7, 20, 36, 8, 16, 4
+    g = torch.Generator().manual_seed(77)
+    S = Lq = L * H * W
+    value = torch.randn(1, S, M, D, generator=g).to(cuda)
+    offsets = (torch.randn(1, Lq, M, L, P, 2, generator=g) * 3).to(cuda)
+    logits = torch.randn(1, Lq, M, L * P, generator=g).to(cuda)
+    ys, xs = torch.meshgrid(torch.linspace(0.5, H - 0.5, H), torch.linspace(0.5, W - 0.5, W), indexing="ij")
+    table = torch.stack((xs / W, ys / H), -1).reshape(H * W, 1, 1, 2).repeat(1, L, P, 1).contiguous().to(cuda)
+    shapes = torch.as_tensor([[H, W]] * L, dtype=torch.long, device=cuda)
+    start = torch.arange(L, device=cuda) * (H * W)
+    o_gen, attn, loc = ops.msda_fused_forward(value, shapes, start, offsets, logits, table, want_aux=True)
+    o_vg = ops.msda_fused_forward(value, shapes, start, offsets, logits, table, grid_hw=(H, W))
+    # aux outputs are only produced by the generic kernel (the view-grid kernel defers the softmax normalisation)
+    _, attn2, loc2 = ops.msda_fused_forward(value, shapes, start, offsets, logits, table, want_aux=True, grid_hw=(H, W))
+    assert torch.equal(attn, attn2) and torch.equal(loc, loc2)
+    assert (o_vg - o_gen).abs().max().item() <= 1e-5
+    ref = co.msda_forward(value.cpu().numpy(), shapes.cpu().numpy(), start.cpu().numpy(), loc.cpu().numpy(),
+                          attn.cpu().numpy())
+    assert np.abs(o_vg.cpu().numpy() - ref).max() <= FP32_ATOL
+    # query subset (view-sharded ranks): rows of views 2..4 only
+    hw = H * W
+    sub = ops.msda_fused_forward(value, shapes, start, offsets[:, 2 * hw:5 * hw].contiguous(),
+                                 logits[:, 2 * hw:5 * hw].contiguous(), table, grid_hw=(H, W))
+    assert torch.equal(sub, o_vg[:, 2 * hw:5 * hw])
