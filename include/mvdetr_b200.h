@@ -111,11 +111,12 @@ MVD_API int mvd_msda_fwd_viewgrid_f32(const float* value, const float* loc, cons
 
 /* View-grid variant of mvd_msda_fused_fwd_f32 below (grid given as host ints; S = L*H*W, Lq = R*H*W).
  * `ref_lm` is the reference table in LEVEL-MAJOR order [L, Lr, P, 2] (query q reads row q % Lr of every level),
- * which lets neighbouring ground cells read neighbouring 32-byte sectors. loc/ref pointers 32-byte aligned. The softmax is evaluated online (running max, one division at the
+ * (Lr must equal H*W: one table row per ground cell). All pointers 16-byte aligned. The softmax is evaluated online (running max, one division at the
  * end), so results agree with mvd_msda_fused_fwd_f32 to rounding; attn_out / loc_out must be NULL here
  * (MVD_ERR_UNSUPPORTED otherwise: callers that need them use mvd_msda_fused_fwd_f32). */
 MVD_API int mvd_msda_fused_fwd_viewgrid_f32(const float* value, const float* offsets, const float* logits,
-                                    const float* ref_lm, int B, int H, int W, int M, int D, int L, int R, int P, int Lr,
+                                    const float* ref_lm, const float* off_bias, const float* logit_bias,
+                                    int B, int H, int W, int M, int D, int L, int R, int P, int Lr,
                                     float* out, float* attn_out, float* loc_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -130,12 +131,15 @@ MVD_API int mvd_msda_fused_fwd_viewgrid_f32(const float* value, const float* off
  *   ref     [Lr, L, P, 2]        normalised reference points, shared by the batch; query q uses row q % Lr
  *                                (MVDeTr: Lr = H*W, the table of mvd/models/mvdetr.py:33-71 before its
  *                                 `.repeat([num_cam,1,1,1])` at :130)
+ *   off_bias   (nullable) [M, L, P, 2]  added to `offsets` first: lets the caller run the `sampling_offsets` Linear as a
+ *   logit_bias (nullable) [M, L, P]     bias-free GEMM (`attention_weights` likewise); same rounding as Linear's acc + b
  *   out     [B, Lq, M*D]
  *   attn_out (nullable) [B, Lq, M, L, P]  softmax-ed weights, written when non-NULL (needed by backward)
  *   loc_out  (nullable) [B, Lq, M, L, P, 2] sampling locations, written when non-NULL
  * ------------------------------------------------------------------------------------------ */
 MVD_API int mvd_msda_fused_fwd_f32(const float* value, const int64_t* shapes, const int64_t* start,
                            const float* offsets, const float* logits, const float* ref,
+                           const float* off_bias, const float* logit_bias,
                            int B, int S, int M, int D, int L, int Lq, int P, int Lr,
                            float* out, float* attn_out, float* loc_out, void* stream);
 
@@ -154,12 +158,16 @@ MVD_API int mvd_msda_fused_fwd_f32(const float* value, const int64_t* shapes, co
  *   (X,Y,Z) = T*(g,1), (x,y) = (X,Y) * (|Z|>1e-8 ? 1/(Z+1e-8) : 1),
  *   ix = ((x+1)*Wi-1)/2, iy = ((y+1)*Hi-1)/2, 4-tap bilinear with zero padding.
  *
- *   `channels_last` != 0 writes dst as [BN, Ho, Wo, C] instead (same values; lets the caller skip a
- *   permute-copy, ref: mvd/models/trans_world_feat.py:92).
+ *   `layout` is a bit set of MVD_WARP_DST_NHWC (dst written as [BN, Ho, Wo, C]: lets the caller skip the
+ *   permute-copy of ref: mvd/models/trans_world_feat.py:92) and MVD_WARP_SRC_NHWC (src read as [BN, Hi, Wi, C],
+ *   C % 4 == 0, 16-byte aligned: every tap is one contiguous C-vector -- the fast path; a torch channels_last
+ *   tensor has this layout). 0 = NCHW in, NCHW out (the kornia contract). Same values in every layout.
  * ------------------------------------------------------------------------------------------ */
+#define MVD_WARP_DST_NHWC 1
+#define MVD_WARP_SRC_NHWC 2
 MVD_API int mvd_warp_fwd_f32(const float* src, const float* Mat,
                      int BN, int C, int Hi, int Wi, int Ho, int Wo,
-                     float* dst, int channels_last, void* stream);
+                     float* dst, int layout, void* stream);
 
 /* Backward of the warp w.r.t. `src` (the backbone trains through it, ref: mvd/models/mvdetr.py:177-195;
  * `Mat` carries no gradient in MVDeTr).  Replaces ATen grid_sampler_2d_backward as reached from kornia.
@@ -167,15 +175,26 @@ MVD_API int mvd_warp_fwd_f32(const float* src, const float* Mat,
 MVD_API int mvd_warp_bwd_f32(const float* grad_dst, const float* Mat,
                      int BN, int C, int Hi, int Wi, int Ho, int Wo,
                      float* grad_src, void* stream);
+/* Same backward for channels-last tensors: grad_dst [BN, Ho, Wo, C] -> grad_src [BN, Hi, Wi, C] (C % 4 == 0),
+ * one 128-bit vector reduction per tap per lane instead of C scalar atomics. */
+MVD_API int mvd_warp_bwd_nhwc_f32(const float* grad_dst, const float* Mat,
+                          int BN, int C, int Hi, int Wi, int Ho, int Wo,
+                          float* grad_src, void* stream);
+
+/* Batched 2-D transpose in[batch][rows][cols] -> out[batch][cols][rows] (fp32, out must not alias in): the
+ * NCHW <-> NHWC relayout ([BN, C, H*W] <-> [BN, H*W, C]) for callers of the warp that hold the other layout
+ * (replaces the permute-copy of ref: mvd/models/trans_world_feat.py:92 when it cannot be avoided). */
+MVD_API int mvd_transpose_f32(const float* in, int batch, int rows, int cols, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused residual add + LayerNorm over the last dimension (caller-side glue of the encoder layer, eval mode):
- *   out[r,:] = LayerNorm(x[r,:] + res[r,:]; eps) * gamma + beta          res may be NULL (plain LayerNorm)
+ *   out[r,:] = LayerNorm(x[r,:] + (res[r,:] + res_bias); eps) * gamma + beta     res may be NULL (plain LayerNorm);
+ *   res_bias [C] may be NULL: it is the bias of the Linear layer that produced `res` when that GEMM ran bias-free
  *   replaces `src = self.norm1(src + self.dropout1(src2))` / `self.norm2(src + self.dropout3(src2))`
  *       ref: mvd/models/deformable_transformer.py:79-80,84-85
  *   x, res, out [rows, C] (out may alias x or res); gamma, beta [C]; C % 4 == 0, C <= 1024, 16-byte aligned.
  * ------------------------------------------------------------------------------------------ */
-MVD_API int mvd_add_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
+MVD_API int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma, const float* beta,
                                   int64_t rows, int C, float eps, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------

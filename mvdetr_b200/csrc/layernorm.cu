@@ -1,4 +1,4 @@
-// Fused residual add + LayerNorm over the last dimension: out[r,:] = LN(x[r,:] + res[r,:]) * gamma + beta.
+// Fused residual add + LayerNorm over the last dimension: out[r,:] = LN(x[r,:] + (res[r,:] + res_bias)) * gamma + beta.
 // The encoder layer does this twice per layer on [N*Hd*Wd, C] tokens (eval mode, dropout = identity):
 //   ref: multiview_detector/models/deformable_transformer.py:79-80 and :84-85
 // torch runs it as an elementwise add (3 x 38.7 MB of traffic) plus a LayerNorm kernel with one 128-thread block
@@ -10,6 +10,7 @@ namespace mvd {
 
 template <int VPL>  // float4 vectors per lane: C <= 128 * VPL
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                            const float* __restrict__ res_bias,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int64_t rows, int C,
                                                             float eps, float* __restrict__ out) {
@@ -28,7 +29,11 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
     if (i < nvec) {
       v[k] = __ldcs(xr + i);
       if (rr) {
-        const float4 r = __ldcs(rr + i);
+        float4 r = __ldcs(rr + i);
+        if (res_bias) {  // res is a bias-free GEMM output: (acc + bias) first, as the Linear layer rounds it
+          const float4 rb = __ldg(reinterpret_cast<const float4*>(res_bias) + i);
+          r.x += rb.x, r.y += rb.y, r.z += rb.z, r.w += rb.w;
+        }
         v[k].x += r.x;
         v[k].y += r.y;
         v[k].z += r.z;
@@ -72,26 +77,29 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
 
 using namespace mvd;
 
-extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const float* gamma, const float* beta,
+extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma,
+                                     const float* beta,
                                      int64_t rows, int C, float eps, float* out, void* stream) {
   if (!x || !gamma || !beta || !out) return MVD_ERR_NULL_POINTER;
   if (rows <= 0 || C <= 0) return MVD_ERR_BAD_SHAPE;
   if ((C & 3) || C > 1024) return MVD_ERR_UNSUPPORTED;
   const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
-                       (res ? reinterpret_cast<uintptr_t>(res) : 0);
+                       (res ? reinterpret_cast<uintptr_t>(res) : 0) |
+                       (res_bias ? reinterpret_cast<uintptr_t>(res_bias) : 0);
+  if (res_bias && !res) return MVD_ERR_NULL_POINTER;
   if (al & 15u) return MVD_ERR_MISALIGNED;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t blocks = ceil_div64(rows, 8);
   if (blocks > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
   if (C <= 128)
-    add_layernorm_kernel<1><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<1><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
   else if (C <= 256)
-    add_layernorm_kernel<2><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<2><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
   else if (C <= 512)
-    add_layernorm_kernel<4><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<4><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
   else
-    add_layernorm_kernel<8><<<(int)blocks, 256, 0, st>>>(x, res, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<8><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
 }

@@ -85,7 +85,8 @@ template <int D, bool FUSED>
 __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
     const float* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ start,
     const float* __restrict__ loc_or_off, const float* __restrict__ attn_or_logit, const float* __restrict__ ref,
-    int S, int M, int L, int Lq, int P, int Lr, int64_t n_pairs, float* __restrict__ out,
+    const float* __restrict__ off_bias, const float* __restrict__ logit_bias, int S, int M, int L, int Lq, int P,
+    int Lr, int64_t n_pairs, float* __restrict__ out,
     float* __restrict__ attn_out, float* __restrict__ loc_out) {
   constexpr int G = D / 4;  // lanes per pair
   constexpr int PAIRS = 256 / G;
@@ -111,13 +112,17 @@ __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
   // FUSED: softmax statistics over the L*P logits of this pair; lane `sub` owns logits sub, sub+G, ...
   float smax = 0.f, ssum = 1.f;
   const float2* rp = nullptr;
+  // optional biases of the two Linear layers (per head m): raw + bias is rounded first, like Linear's acc + b
+  const float* lbp = (FUSED && logit_bias) ? logit_bias + (int64_t)m * LP : nullptr;
+  const float2* obp = (FUSED && off_bias) ? reinterpret_cast<const float2*>(off_bias) + (int64_t)m * LP : nullptr;
+  auto logit = [&](int i) { return lbp ? __ldg(ap + i) + __ldg(lbp + i) : __ldg(ap + i); };
   if (FUSED) {
     float mx = -INFINITY;
-    for (int i = sub; i < LP; i += G) mx = fmaxf(mx, __ldg(ap + i));
+    for (int i = sub; i < LP; i += G) mx = fmaxf(mx, logit(i));
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o, G));
     float sum = 0.f;
-    for (int i = sub; i < LP; i += G) sum += expf(__ldg(ap + i) - mx);
+    for (int i = sub; i < LP; i += G) sum += expf(logit(i) - mx);
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o, G);
     smax = mx;
@@ -138,11 +143,16 @@ __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
       float2 xy;
       float a;
       if (FUSED) {
-        const float2 off = ld_stream2(reinterpret_cast<const float*>(lp + s));
+        float2 off = ld_stream2(reinterpret_cast<const float*>(lp + s));
+        if (obp) {
+          const float2 ob = __ldg(obp + s);
+          off.x += ob.x;
+          off.y += ob.y;
+        }
         const float2 r = __ldg(rp + s);
         xy.x = r.x + off.x / fW;
         xy.y = r.y + off.y / fH;
-        a = expf(__ldg(ap + s) - smax) / ssum;
+        a = expf(logit(s) - smax) / ssum;
         if (valid) {
           if (attn_out) attn_out[pair * LP + s] = a;
           if (loc_out) reinterpret_cast<float2*>(loc_out)[pair * LP + s] = xy;
@@ -217,26 +227,26 @@ static int launch_scalar(const T* value, const int64_t* shapes, const int64_t* s
 
 template <int D, bool FUSED>
 static int launch_vec4(const float* value, const int64_t* shapes, const int64_t* start, const float* loc,
-                       const float* attn, const float* ref, int B, int S, int M, int L, int Lq, int P, int Lr,
+                       const float* attn, const float* ref, const float* off_bias, const float* logit_bias, int B, int S, int M, int L, int Lq, int P, int Lr,
                        float* out, float* attn_out, float* loc_out, cudaStream_t st) {
   constexpr int PAIRS = 256 / (D / 4);
   const int64_t n_pairs = (int64_t)B * Lq * M;
   const int64_t blocks = ceil_div64(n_pairs, PAIRS);
   if (blocks > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
   msda_fwd_vec4_kernel<D, FUSED><<<(int)blocks, 256, L * sizeof(Level), st>>>(
-      value, shapes, start, loc, attn, ref, S, M, L, Lq, P, Lr, n_pairs, out, attn_out, loc_out);
+      value, shapes, start, loc, attn, ref, off_bias, logit_bias, S, M, L, Lq, P, Lr, n_pairs, out, attn_out, loc_out);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
 }
 
 template <bool FUSED>
 static int dispatch_vec4(const float* value, const int64_t* shapes, const int64_t* start, const float* loc,
-                         const float* attn, const float* ref, int B, int S, int M, int D, int L, int Lq, int P,
+                         const float* attn, const float* ref, const float* off_bias, const float* logit_bias, int B, int S, int M, int D, int L, int Lq, int P,
                          int Lr, float* out, float* attn_out, float* loc_out, cudaStream_t st) {
 #define MVD_CASE(DD)                                                                                              \
   case DD:                                                                                                        \
-    return launch_vec4<DD, FUSED>(value, shapes, start, loc, attn, ref, B, S, M, L, Lq, P, Lr, out, attn_out,     \
-                                  loc_out, st)
+    return launch_vec4<DD, FUSED>(value, shapes, start, loc, attn, ref, off_bias, logit_bias, B, S, M, L, Lq, P,  \
+                                  Lr, out, attn_out, loc_out, st)
   switch (D) {
     MVD_CASE(4);
     MVD_CASE(8);
@@ -272,7 +282,7 @@ extern "C" int mvd_msda_fwd_f32(const float* value, const int64_t* shapes, const
   if (int e = check_dims(B, S, M, D, L, Lq, P)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (vec4_ok(D, S) && aligned16(value) && aligned16(out) && aligned8(loc))
-    return dispatch_vec4<false>(value, shapes, start, loc, attn, nullptr, B, S, M, D, L, Lq, P, 1, out, nullptr,
+    return dispatch_vec4<false>(value, shapes, start, loc, attn, nullptr, nullptr, nullptr, B, S, M, D, L, Lq, P, 1, out, nullptr,
                                 nullptr, st);
   return launch_scalar<float>(value, shapes, start, loc, attn, B, S, M, D, L, Lq, P, out, st);
 }
@@ -286,16 +296,17 @@ extern "C" int mvd_msda_fwd_f64(const double* value, const int64_t* shapes, cons
 }
 
 extern "C" int mvd_msda_fused_fwd_f32(const float* value, const int64_t* shapes, const int64_t* start,
-                                      const float* offsets, const float* logits, const float* ref, int B, int S,
-                                      int M, int D, int L, int Lq, int P, int Lr, float* out, float* attn_out,
-                                      float* loc_out, void* stream) {
+                                      const float* offsets, const float* logits, const float* ref,
+                                      const float* off_bias, const float* logit_bias, int B, int S, int M, int D,
+                                      int L, int Lq, int P, int Lr, float* out, float* attn_out, float* loc_out,
+                                      void* stream) {
   if (!value || !shapes || !start || !offsets || !logits || !ref || !out) return MVD_ERR_NULL_POINTER;
   if (int e = check_dims(B, S, M, D, L, Lq, P)) return e;
   if (Lr <= 0) return MVD_ERR_BAD_SHAPE;
   if (!vec4_ok(D, S)) return MVD_ERR_UNSUPPORTED;
   if (!aligned16(value) || !aligned16(out) || !aligned8(offsets) || !aligned8(ref) ||
-      (loc_out && !aligned8(loc_out)))
+      (loc_out && !aligned8(loc_out)) || (off_bias && !aligned8(off_bias)))
     return MVD_ERR_MISALIGNED;
-  return dispatch_vec4<true>(value, shapes, start, offsets, logits, ref, B, S, M, D, L, Lq, P, Lr, out, attn_out,
+  return dispatch_vec4<true>(value, shapes, start, offsets, logits, ref, off_bias, logit_bias, B, S, M, D, L, Lq, P, Lr, out, attn_out,
                              loc_out, (cudaStream_t)stream);
 }

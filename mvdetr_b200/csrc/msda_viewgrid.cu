@@ -3,36 +3,45 @@
 //   (ref: multiview_detector/models/trans_world_feat.py:92, multiview_detector/models/mvdetr.py:129-130).
 // Same maths as the generic kernels of msda_fwd.cu (ref: ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299).
 //
-// Why a second kernel: the generic gather goes through L1 one 64-byte head-pixel (D=16) per 128-byte line, which
-// ncu shows issue- and L1-bound at ~12 % of the algorithmic-HBM roofline (profiles/r01a_*). Here the R queries that sit
-// on the same ground cell share their reference point, so a block that owns a TH x TW tile of cells x all R views x one
-// head m touches, per level, only a (TH+2*HALO) x (TW+2*HALO) pixel window of value[:, level, :, m, :]:
-//   * the window is staged in shared memory by ONE TMA tensor copy per level (5-D map d,m,x,y,level; box D x 1 x BW x
-//     BH x 1). Out-of-map coordinates are zero-filled by the TMA unit, which IS the op's zero padding, so in-window
-//     samples need no corner masks;
-//   * windows are double buffered (level l+1 lands while level l is consumed), completion by mbarrier tx-count;
-//   * one thread owns one (query, head) pair and all D channels: no cross-lane shuffles and no redundant sample
-//     arithmetic. Each corner is D/4 128-bit shared loads; a per-lane rotation of the channel quads makes
-//     neighbouring pixels hit disjoint bank groups, and the accumulators simply stay in that rotated order until
-//     the final store;
-//   * loc/attn (or offsets/logits when FUSED) are read exactly once, one 32-byte sector per (pair, level), and
-//     prefetched into L2 one level ahead (no registers held across the level);
-//   * sampling offsets are learned and unbounded: a sample whose 2x2 footprint is not inside the window takes the
-//     masked global-memory path of the generic kernel, so the staging changes speed, never results.
+// A block owns a TH x TW tile of ground cells x all R views x ONE head m; one thread owns one (query, head) pair and
+// all D channels (no cross-lane traffic, no redundant sample arithmetic). Per level, EVERYTHING the block reads
+// arrives in shared memory through the TMA unit, two stages deep, one mbarrier transaction count per stage:
+//   * the (TH+2*HALO) x (TW+2*HALO) pixel window of value[:, level, :, m, :]  (5-D map d,m,x,y,level; out-of-map
+//     coordinates are zero-filled by the TMA unit, which IS the op's zero padding: in-window samples need no masks);
+//   * the tile's sampling locations / offsets  [R][TH][TW][P][2]  (5-D map over loc: box 2P x 1 x TW x TH x R);
+//   * the tile's attention weights / logits     [R][TH][TW][P]     (same, box P x 1 x TW x TH x R);
+//   * FUSED: the tile's rows of the level-major reference table [TH][TW][P][2] (3-D map).
+// r01a ncu (profiles/r01a_ncu_full_summary.txt) showed why: with per-lane global loads of loc/attn every lane touched
+// its own 128-byte line (33 L1 wavefronts per request, 26 % of all data-pipe wavefronts), the loads stalled every
+// level on L2 latency (long_scoreboard 22 % of samples) and the 256-bit staging registers spilled.
+// Pipeline: no block-wide barrier in the level loop. Consumer warps arrive on the stage's `empty` mbarrier when done
+// with a level; the refill of that stage (level l+2) is issued by one lane of warp (l mod nwarps) after it has seen
+// `empty` complete, so only that warp ever waits for the slowest one.
+// Corners are 128-bit shared loads with a per-lane rotation of the channel quads (neighbouring pixels hit disjoint
+// bank groups; the accumulators stay in rotated order until the final store). Samples outside the level read a
+// zeroed pad region with zero weights (exactly 0, no branch); samples whose 2x2 footprint leaves the window take a
+// masked global-memory path, so staging changes speed, never results.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace mvd {
 
-constexpr int kHalo = 6;       // pixels around the tile kept in the window (default init samples +-4 px: ms_deform_attn.py:62-77)
+// legacy kernel (msda_viewgrid_v1.cu), reachable with MVD_VIEWGRID_IMPL=1 for A/B timing
+int viewgrid_v1(bool fused, const float* value, const float* loc, const float* attn, const float* ref, int B, int H,
+                int W, int M, int D, int L, int R, int P, int Lr, float* out, cudaStream_t st);
+
+namespace {
+
+constexpr int kHalo = 6;          // pixels around the tile kept in the window (default init samples +-4 px: ms_deform_attn.py:62-77)
 constexpr int kMaxThreads = 448;  // 2 blocks/SM at <= 72 registers
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_tiled_fn() {
+EncodeTiledFn encode_tiled_fn() {
   static EncodeTiledFn fn = nullptr;  // idempotent lookup; a race only repeats it
   if (!fn) {
     void* p = nullptr;
@@ -51,6 +60,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait: a TMA copy that never completes (bad descriptor, lost transaction) must surface as a launch failure,
 // not as a hung GPU. 2^26 polls (each try_wait already sleeps up to a hardware time limit) is minutes, not microseconds.
@@ -77,54 +89,30 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
       : "memory");
 }
-
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], "
+      "[%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
 }
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
 struct VgParams {
-  const float* value;   // [B, L*H*W, M, D]  (global fallback path)
-  const float* loc;     // loc [B,Lq,M,L,P,2]      or offsets when FUSED
-  const float* attn;    // attn [B,Lq,M,L,P]       or logits when FUSED
-  const float* ref;     // FUSED: [L, Lr, P, 2]  (level-major)
-  float* out;           // [B, Lq, M*D]
-  float* attn_out;      // FUSED, nullable
-  float* loc_out;       // FUSED, nullable
-  int H, W, M, L, R, Lr;
+  const float* value;  // [B, L*H*W, M, D]  (global fallback path)
+  float* out;          // [B, Lq, M*D]
+  const float* off_bias;    // FUSED, nullable: [M, L, P, 2] added to the raw offsets
+  const float* logit_bias;  // FUSED, nullable: [M, L, P]
+  int H, W, M, L, R;
   int TH, TW, tiles_x;
-  int BW, BH;           // window = tile + 2*halo
+  int BW, BH;                                 // window = tile + 2*halo
+  uint32_t off_a, off_b, off_ref;             // byte offsets of the per-stage regions (window is at 0)
+  uint32_t stage_bytes, zero_off, zero_bytes; // stage pitch; zero pad region (after both stages)
+  uint32_t tx_bytes;                          // bytes landing per stage
 };
-
-// One (pair, level) worth of sampling inputs held in registers.
-template <int P>
-struct LevelIn {
-  float xy[2 * P];
-  float a[P];
-};
-
-template <int P>
-__device__ __forceinline__ void load_level(LevelIn<P>& r, const float* __restrict__ lp, const float* __restrict__ ap) {
-  // loc: P*8 bytes = whole 32-byte sectors, one 256-bit request each (the L1 tag stage is the scarce resource here:
-  // every lane touches its own line, so requests, not bytes, are what costs)
-#pragma unroll
-  for (int i = 0; i < P / 4; ++i) ld_stream8(lp + 8 * i, r.xy + 8 * i);
-  if (P == 4) {
-    const float4 v = ld_stream4(ap);
-    r.a[0] = v.x;
-    r.a[1] = v.y;
-    r.a[2] = v.z;
-    r.a[3] = v.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < P / 8; ++i) ld_stream8(ap + 8 * i, r.a + 8 * i);
-  }
-}
 
 // acc[k] += w1*v1 + w2*v2 + w3*v3 + w4*v4 for one channel quad
 __device__ __forceinline__ void fma4(float4& acc, float w1, const float4& v1, float w2, const float4& v2, float w3,
@@ -135,40 +123,77 @@ __device__ __forceinline__ void fma4(float4& acc, float w1, const float4& v1, fl
   acc.w = fmaf(w4, v4.w, fmaf(w3, v3.w, fmaf(w2, v2.w, fmaf(w1, v1.w, acc.w))));
 }
 
+// Reads N floats (N % 4 == 0) of this thread's record from a [thread][N] shared array with 128-bit loads. For
+// N == 8 the two halves are fetched in an order that depends on bit 2 of the lane, so the 8 lanes of a quarter-warp
+// phase cover all 32 banks (records are 32 bytes apart: lanes j and j+4 would otherwise collide).
+template <int N>
+__device__ __forceinline__ void read_record(const unsigned char* base, int idx, int lane, float* dst) {
+  const float4* p = reinterpret_cast<const float4*>(base + (size_t)idx * N * 4);
+  if (N == 8) {
+    const int h = (lane >> 2) & 1;
+    const float4 a = p[h], b = p[h ^ 1];
+    const float4 lo = h ? b : a, hi = h ? a : b;
+    dst[0] = lo.x, dst[1] = lo.y, dst[2] = lo.z, dst[3] = lo.w;
+    dst[4] = hi.x, dst[5] = hi.y, dst[6] = hi.z, dst[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+      const float4 a = p[i];
+      dst[4 * i] = a.x, dst[4 * i + 1] = a.y, dst[4 * i + 2] = a.z, dst[4 * i + 3] = a.w;
+    }
+  }
+}
+
 template <int D, int P, bool FUSED>
 __global__ void __launch_bounds__(kMaxThreads, 2)
-    msda_fwd_viewgrid_kernel(const __grid_constant__ CUtensorMap tmap, const VgParams prm) {
-  constexpr int NQ = D / 4;             // channel quads (16-byte pieces) per head-pixel
+    msda_vg_kernel(const __grid_constant__ CUtensorMap tm_val, const __grid_constant__ CUtensorMap tm_a,
+                   const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_ref,
+                   const VgParams prm) {
+  constexpr int NQ = D / 4;  // channel quads (16-byte pieces) per head-pixel
   constexpr int PX_BYTES = D * 4;
-  constexpr int PC = 4;                 // samples prepared together (P is a multiple of 4)
+  constexpr int PC = 4;  // samples prepared together (P is a multiple of 4)
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ __align__(8) unsigned long long s_bar[4];  // full[0], full[1], empty[0], empty[1]
 
   const int H = prm.H, W = prm.W, M = prm.M, L = prm.L, R = prm.R;
   const int BW = prm.BW, BH = prm.BH;
-  const int win_bytes = BW * BH * PX_BYTES;
-  const uint32_t win0 = smem_u32(smem_raw);
-  const uint32_t bar0 = smem_u32(&s_bar[0]);
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = smem_u32(&s_bar[2]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
   const int tile = blockIdx.x;
   const int ty0 = (tile / prm.tiles_x) * prm.TH, tx0 = (tile % prm.tiles_x) * prm.TW;
   const int m = blockIdx.y, b = blockIdx.z;
   const int wy0 = ty0 - kHalo, wx0 = tx0 - kHalo;  // window origin in level pixels (may be negative: TMA zero fill)
 
+  auto issue_level = [&](int lv) {  // one lane: everything level `lv` needs -> stage lv & 1
+    const uint32_t st = smem0 + (uint32_t)(lv & 1) * prm.stage_bytes, bar = bar_full + 8u * (uint32_t)(lv & 1);
+    mbar_expect_tx(bar, prm.tx_bytes);
+    tma_load_5d(st, &tm_val, bar, 0, m, wx0, wy0, b * L + lv);
+    tma_load_5d(st + prm.off_a, &tm_a, bar, lv * 2 * P, m, tx0, ty0, b * R);
+    tma_load_5d(st + prm.off_b, &tm_b, bar, lv * P, m, tx0, ty0, b * R);
+    if (FUSED) tma_load_3d(st + prm.off_ref, &tm_ref, bar, tx0 * 2 * P, ty0, lv);
+  };
+
   if (threadIdx.x == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    prefetch_tmap(&tm_val);
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+    if (FUSED) prefetch_tmap(&tm_ref);
+    mbar_init(bar_full, 1);
+    mbar_init(bar_full + 8, 1);
+    mbar_init(bar_empty, (uint32_t)nwarps);
+    mbar_init(bar_empty + 8, (uint32_t)nwarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  for (uint32_t i = threadIdx.x * 16u; i < prm.zero_bytes; i += blockDim.x * 16u)
+    *reinterpret_cast<float4*>(smem_raw + prm.zero_off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int nl = L < 2 ? L : 2;
-    for (int l = 0; l < nl; ++l) {
-      mbar_expect_tx(bar0 + 8 * l, (uint32_t)win_bytes);
-      tma_load_5d(win0 + l * win_bytes, &tmap, bar0 + 8 * l, 0, m, wx0, wy0, b * L + l);
-    }
+    issue_level(0);
+    if (L > 1) issue_level(1);
   }
 
   // ---- this thread's (query, head) pair ----
@@ -181,16 +206,10 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
   const int q = r * HW + y * W + x;
   const int64_t Lq = (int64_t)R * HW;
   const int64_t pair = active ? ((int64_t)b * Lq + q) * M + m : 0;
-  const int LP = L * P;
-  const float* lp = prm.loc + pair * LP * 2;
-  const float* ap = prm.attn + pair * LP;
-  // FUSED: reference table is level-major [L, Lr, P, 2] so that neighbouring cells read neighbouring sectors
-  const float* rp = FUSED ? prm.ref + (int64_t)(active ? q % prm.Lr : 0) * P * 2 : nullptr;
   const float fH = (float)H, fW = (float)W;
 
   // per-lane rotation of the channel quads (bank-conflict avoidance, see header): quad k of this thread's
   // accumulator holds channels 4*((k+rot)%NQ) .. +3
-  const int lane = threadIdx.x & 31;
   const int rot = (NQ >= 8) ? (lane & (NQ - 1)) : (NQ == 4 ? ((lane >> 1) & 3) : ((lane >> 2) & (NQ - 1)));
   int qoff[NQ];  // byte offset of quad k inside a head-pixel
 #pragma unroll
@@ -209,26 +228,44 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
   const int rowb = BW * PX_BYTES;
 
   for (int l = 0; l < L; ++l) {
-    LevelIn<P> cur, refl;
+    const int s = l & 1;
+    const uint32_t ph = (uint32_t)((l >> 1) & 1);
+    const unsigned char* win = smem_raw + (size_t)s * prm.stage_bytes;
+    const int zoff = (int)prm.zero_off - (int)(s * prm.stage_bytes);  // zero pad relative to this stage's window
+    mbar_wait(bar_full + 8u * s, ph);
+
+    float xy[2 * P], aw[P];
     if (active) {
-      load_level<P>(cur, lp + l * P * 2, ap + l * P);
+      read_record<2 * P>(win + prm.off_a, threadIdx.x, lane, xy);
+      read_record<P>(win + prm.off_b, threadIdx.x, lane, aw);
       if (FUSED) {
+        float rf[2 * P];
+        read_record<2 * P>(win + prm.off_ref, pos, lane, rf);
+        if (prm.off_bias) {  // block-uniform addresses: one broadcast wavefront each
+          const float* ob = prm.off_bias + ((int64_t)m * L + l) * 2 * P;
 #pragma unroll
-        for (int i = 0; i < P / 4; ++i) ldg8(rp + (int64_t)l * prm.Lr * P * 2 + 8 * i, refl.xy + 8 * i);
-      }
-      if (l + 1 < L) {  // next level's sectors: HBM -> L2 now, so that its loads are L2 hits
-        prefetch_l2(lp + (l + 1) * P * 2);
-        if (P > 4) prefetch_l2(lp + (l + 1) * P * 2 + 8);
-        if (((l + 1) * P) % 8 == 0) prefetch_l2(ap + (l + 1) * P);
+          for (int i = 0; i < 2 * P; ++i) xy[i] += __ldg(ob + i);
+        }
+        if (prm.logit_bias) {
+          const float* lb = prm.logit_bias + ((int64_t)m * L + l) * P;
+#pragma unroll
+          for (int i = 0; i < P; ++i) aw[i] += __ldg(lb + i);
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          // same operation order as the reference module: ref + off / (W, H)
+          xy[2 * i] = rf[2 * i] + xy[2 * i] / fW;
+          xy[2 * i + 1] = rf[2 * i + 1] + xy[2 * i + 1] / fH;
+        }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < P; ++i) cur.xy[2 * i] = cur.xy[2 * i + 1] = cur.a[i] = refl.xy[2 * i] = refl.xy[2 * i + 1] = 0.f;
+      for (int i = 0; i < P; ++i) xy[2 * i] = xy[2 * i + 1] = aw[i] = 0.f;
     }
     if (FUSED) {
-      float lm = cur.a[0];
+      float lm = aw[0];
 #pragma unroll
-      for (int i = 1; i < P; ++i) lm = fmaxf(lm, cur.a[i]);
+      for (int i = 1; i < P; ++i) lm = fmaxf(lm, aw[i]);
       const float new_max = fmaxf(run_max, lm);
       const float sc = (run_max == -INFINITY) ? 0.f : exp2f((run_max - new_max) * kLog2e);
       run_max = new_max;
@@ -242,46 +279,40 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
       }
 #pragma unroll
       for (int i = 0; i < P; ++i) {
-        cur.a[i] = (new_max == -INFINITY) ? 0.f : exp2f((cur.a[i] - new_max) * kLog2e);
-        run_sum += cur.a[i];
-        // same operation order as the reference module: ref + off / (W, H)
-        cur.xy[2 * i] = refl.xy[2 * i] + cur.xy[2 * i] / fW;
-        cur.xy[2 * i + 1] = refl.xy[2 * i + 1] + cur.xy[2 * i + 1] / fH;
+        aw[i] = (new_max == -INFINITY) ? 0.f : exp2f((aw[i] - new_max) * kLog2e);
+        run_sum += aw[i];
       }
     }
-    mbar_wait(bar0 + 8 * (l & 1), (uint32_t)((l >> 1) & 1));
-    const unsigned char* win = smem_raw + (l & 1) * win_bytes;
 
 #pragma unroll
     for (int pc = 0; pc < P; pc += PC) {
       // ---- sample arithmetic for PC samples (ref: ms_deform_im2col_cuda.cuh:285-288, :33-84) ----
       float w1[PC], w2[PC], w3[PC], w4[PC];
-      int off[PC], h0[PC], w0[PC];
-      unsigned valid = 0u, inwin = 0u;
+      int off[PC];
+      unsigned far = 0u;  // valid samples whose footprint is not inside the window
 #pragma unroll
       for (int i = 0; i < PC; ++i) {
-        const float a = cur.a[pc + i];
+        const float a = aw[pc + i];
         // product rounded before the subtraction, as the reference's float*int - 0.5 does
-        const float h_im = __fsub_rn(__fmul_rn(cur.xy[2 * (pc + i) + 1], fH), 0.5f);
-        const float w_im = __fsub_rn(__fmul_rn(cur.xy[2 * (pc + i)], fW), 0.5f);
-        const bool v = h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;  // false for NaN
+        const float h_im = __fsub_rn(__fmul_rn(xy[2 * (pc + i) + 1], fH), 0.5f);
+        const float w_im = __fsub_rn(__fmul_rn(xy[2 * (pc + i)], fW), 0.5f);
+        // false for NaN and for threads without a query (tile overhang): those behave like outside samples
+        const bool v = active && h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
         const float hf = floorf(h_im), wf = floorf(w_im);
-        h0[i] = v ? (int)hf : 0;
-        w0[i] = v ? (int)wf : 0;
+        const int h0 = v ? (int)hf : 0, w0 = v ? (int)wf : 0;
         const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-        w1[i] = hh * hw * a;
-        w2[i] = hh * lw * a;
-        w3[i] = lh * hw * a;
-        w4[i] = lh * lw * a;
-        const int dx = w0[i] - wx0, dy = h0[i] - wy0;
-        const bool in = v && (unsigned)dx < (unsigned)(BW - 1) && (unsigned)dy < (unsigned)(BH - 1);
-        off[i] = in ? (dy * BW + dx) * PX_BYTES : 0;
-        valid |= (unsigned)v << i;
-        inwin |= (unsigned)in << i;
+        // a sample outside the level contributes exactly 0: zero weights on the zero pad (never NaN * 0)
+        w1[i] = v ? hh * hw * a : 0.f;
+        w2[i] = v ? hh * lw * a : 0.f;
+        w3[i] = v ? lh * hw * a : 0.f;
+        w4[i] = v ? lh * lw * a : 0.f;
+        const int dx = w0 - wx0, dy = h0 - wy0;
+        const bool in = (unsigned)dx < (unsigned)(BW - 1) && (unsigned)dy < (unsigned)(BH - 1);
+        off[i] = v ? (in ? (dy * BW + dx) * PX_BYTES : 0) : zoff;
+        far |= (unsigned)(v && !in) << i;
       }
-      const bool all_in = !active || inwin == (1u << PC) - 1u;
-      if (__all_sync(FULL, all_in)) {
-        // ---- fast path: every sample of every lane has its 2x2 footprint in the window; no branches ----
+      if (__all_sync(FULL, far == 0u)) {
+        // ---- fast path: every valid sample of every lane has its 2x2 footprint in the window; no branches ----
 #pragma unroll
         for (int i = 0; i < PC; ++i) {
 #pragma unroll
@@ -298,8 +329,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
         // ---- mixed path: per sample, window or masked global loads (generic-kernel semantics) ----
 #pragma unroll
         for (int i = 0; i < PC; ++i) {
-          if (!((valid >> i) & 1u)) continue;
-          if ((inwin >> i) & 1u) {
+          if (!((far >> i) & 1u)) {
 #pragma unroll
             for (int k = 0; k < NQ; ++k) {
               const unsigned char* pk = win + off[i] + qoff[k];
@@ -310,8 +340,11 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
               fma4(acc[k], w1[i], v1, w2[i], v2, w3[i], v3, w4[i], v4);
             }
           } else {
-            const bool top = h0[i] >= 0, bot = h0[i] + 1 <= H - 1, lef = w0[i] >= 0, rig = w0[i] + 1 <= W - 1;
-            const float* p00 = vb + ((int64_t)l * HW + (int64_t)h0[i] * W + w0[i]) * stride_px;
+            // rare path: recompute the top-left pixel instead of keeping it in registers across the fast path
+            const int h0 = (int)floorf(__fsub_rn(__fmul_rn(xy[2 * (pc + i) + 1], fH), 0.5f));
+            const int w0 = (int)floorf(__fsub_rn(__fmul_rn(xy[2 * (pc + i)], fW), 0.5f));
+            const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
+            const float* p00 = vb + ((int64_t)l * HW + (int64_t)h0 * W + w0) * stride_px;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < NQ; ++k) {
@@ -327,11 +360,14 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
         }
       }
     }
-    __syncthreads();  // every thread is done with this stage's window
-    if (threadIdx.x == 0 && l + 2 < L) {
+
+    // ---- release the stage; one warp (rotating) refills it with level l+2 once every warp has released it ----
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8u * s);
+    if (l + 2 < L && warp == l % nwarps && lane == 0) {
+      mbar_wait(bar_empty + 8u * s, ph);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of this stage -> async-proxy refill
-      mbar_expect_tx(bar0 + 8 * (l & 1), (uint32_t)win_bytes);
-      tma_load_5d(win0 + (l & 1) * win_bytes, &tmap, bar0 + 8 * (l & 1), 0, m, wx0, wy0, b * L + l + 2);
+      issue_level(l + 2);
     }
   }
 
@@ -354,92 +390,143 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
 
 struct VgPlan {
   int TH, TW, BW, BH, tiles_x, tiles_y, threads;
+  uint32_t off_a, off_b, off_ref, stage_bytes, zero_off, zero_bytes, tx_bytes;
   size_t smem;
 };
 
+inline uint32_t up128(size_t v) { return (uint32_t)((v + 127) & ~(size_t)127); }
+
 // Tile = TH x TW ground cells with TH*TW*R <= kMaxThreads threads; prefers 64 cells (4x16), 32 (4x8) for many views.
-static bool plan_viewgrid(int H, int W, int D, int R, VgPlan* pl) {
+bool plan_viewgrid(int D, int R, int P, bool fused, VgPlan* pl) {
   int TH = 4, TW = 16;
   while (TH * TW * R > kMaxThreads && TW > 4) TW >>= 1;
   while (TH * TW * R > kMaxThreads && TH > 1) TH >>= 1;
-  if (TH * TW * R > kMaxThreads) return false;
+  if (TH * TW * R > kMaxThreads || R > 256) return false;
   pl->TH = TH;
   pl->TW = TW;
   pl->BW = TW + 2 * kHalo;
   pl->BH = TH + 2 * kHalo;
-  pl->tiles_x = (W + TW - 1) / TW;
-  pl->tiles_y = (H + TH - 1) / TH;
   pl->threads = ((TH * TW * R + 31) / 32) * 32;
-  pl->smem = (size_t)2 * pl->BW * pl->BH * D * 4;
-  return pl->BW <= 256 && pl->BH <= 256;
+  const size_t nbox = (size_t)TH * TW * R;
+  const size_t win = (size_t)pl->BW * pl->BH * D * 4, a = nbox * 2 * P * 4, b = nbox * P * 4,
+               rf = fused ? (size_t)TH * TW * 2 * P * 4 : 0;
+  pl->off_a = up128(win);
+  pl->off_b = pl->off_a + up128(a);
+  pl->off_ref = pl->off_b + up128(b);
+  pl->stage_bytes = pl->off_ref + up128(rf);
+  pl->tx_bytes = (uint32_t)(win + a + b + rf);
+  pl->zero_off = 2 * pl->stage_bytes;
+  pl->zero_bytes = up128((size_t)pl->BW * D * 4 + 2 * D * 4);  // reach of a 2x2 footprint from its top-left pixel
+  pl->smem = (size_t)pl->zero_off + pl->zero_bytes;
+  return pl->smem <= 227 * 1024 && 2 * P * TW <= 256;
 }
 
-static int make_value_map(const float* value, int B, int H, int W, int M, int D, int L, const VgPlan& pl,
-                          CUtensorMap* map) {
+int encode(CUtensorMap* map, const float* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstr,
+           const cuuint32_t* box) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return MVD_ERR_NO_DEVICE;
-  const cuuint64_t gdim[5] = {(cuuint64_t)D, (cuuint64_t)M, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * L};
-  const cuuint64_t gstr[4] = {(cuuint64_t)D * 4, (cuuint64_t)M * D * 4, (cuuint64_t)W * M * D * 4,
-                              (cuuint64_t)H * W * M * D * 4};
-  const cuuint32_t box[5] = {(cuuint32_t)D, 1u, (cuuint32_t)pl.BW, (cuuint32_t)pl.BH, 1u};
   const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
-  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(value), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] % 16 != 0) return MVD_ERR_UNSUPPORTED;
+  const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS ? MVD_OK : MVD_ERR_UNSUPPORTED;
 }
 
 template <int D, int P, bool FUSED>
-static int launch_viewgrid(const CUtensorMap& map, const VgParams& prm, const VgPlan& pl, int B, cudaStream_t st) {
-  auto kern = msda_fwd_viewgrid_kernel<D, P, FUSED>;
+int launch_vg(const CUtensorMap* maps, const VgParams& prm, const VgPlan& pl, int tiles, int B, cudaStream_t st) {
+  auto kern = msda_vg_kernel<D, P, FUSED>;
   MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  dim3 grid((unsigned)(pl.tiles_x * pl.tiles_y), (unsigned)prm.M, (unsigned)B);
-  kern<<<grid, pl.threads, pl.smem, st>>>(map, prm);
+  dim3 grid((unsigned)tiles, (unsigned)prm.M, (unsigned)B);
+  kern<<<grid, pl.threads, pl.smem, st>>>(maps[0], maps[1], maps[2], maps[3], prm);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
 }
 
+bool use_v1() {
+  const char* e = getenv("MVD_VIEWGRID_IMPL");
+  return e && e[0] == '1';
+}
+
 template <bool FUSED>
-static int viewgrid_dispatch(const float* value, const float* loc, const float* attn, const float* ref, int B, int H,
-                             int W, int M, int D, int L, int R, int P, int Lr, float* out, float* attn_out,
-                             float* loc_out, cudaStream_t st) {
+int viewgrid_dispatch(const float* value, const float* loc, const float* attn, const float* ref,
+                      const float* off_bias, const float* logit_bias, int B, int H, int W, int M, int D, int L, int R,
+                      int P, int Lr, float* out, cudaStream_t st) {
   if (B <= 0 || H <= 0 || W <= 0 || M <= 0 || D <= 0 || L <= 0 || R <= 0 || P <= 0) return MVD_ERR_BAD_SHAPE;
   if ((int64_t)B * L * H * W * M * D > 0x7fffffffLL || (int64_t)B * R * H * W * M * L * P * 2 > 0x7fffffffffLL)
     return MVD_ERR_BAD_SHAPE;
   if (M > 65535 || B > 65535) return MVD_ERR_BAD_SHAPE;
   if (!((D == 8 || D == 16 || D == 32) && (P == 4 || P == 8))) return MVD_ERR_UNSUPPORTED;
+  if (use_v1() && !off_bias && !logit_bias)
+    return viewgrid_v1(FUSED, value, loc, attn, ref, B, H, W, M, D, L, R, P, Lr, out, st);
+  if (FUSED && Lr != H * W) return MVD_ERR_UNSUPPORTED;  // table rows must be the grid cells (mvdetr.py:33-71)
   const uintptr_t al = reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(loc) |
                        reinterpret_cast<uintptr_t>(attn) | reinterpret_cast<uintptr_t>(out) |
-                       reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(loc_out) |
-                       reinterpret_cast<uintptr_t>(attn_out);
-  if ((al & 15u) || ((reinterpret_cast<uintptr_t>(loc) | reinterpret_cast<uintptr_t>(ref)) & 31u) ||
-      (P == 8 && (reinterpret_cast<uintptr_t>(attn) & 31u)))
-    return MVD_ERR_MISALIGNED;
+                       reinterpret_cast<uintptr_t>(ref);
+  if (al & 15u) return MVD_ERR_MISALIGNED;
   VgPlan pl;
-  if (!plan_viewgrid(H, W, D, R, &pl)) return MVD_ERR_UNSUPPORTED;
-  alignas(64) CUtensorMap map;
-  if (int e = make_value_map(value, B, H, W, M, D, L, pl, &map)) return e;
+  if (!plan_viewgrid(D, R, P, FUSED, &pl)) return MVD_ERR_UNSUPPORTED;
+  pl.tiles_x = (W + pl.TW - 1) / pl.TW;
+  pl.tiles_y = (H + pl.TH - 1) / pl.TH;
+
+  alignas(64) CUtensorMap maps[4];
+  const cuuint64_t u = 1;
+  {  // value [B*L][H][W][M][D]
+    const cuuint64_t gdim[5] = {u * D, u * M, u * W, u * H, u * B * L};
+    const cuuint64_t gstr[4] = {u * D * 4, u * M * D * 4, u * W * M * D * 4, u * H * W * M * D * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)D, 1u, (cuuint32_t)pl.BW, (cuuint32_t)pl.BH, 1u};
+    if (int e = encode(&maps[0], value, 5, gdim, gstr, box)) return e;
+  }
+  {  // loc / offsets [B*R][H][W][M][L*P*2]
+    const cuuint64_t n = u * L * P * 2;
+    const cuuint64_t gdim[5] = {n, u * M, u * W, u * H, u * B * R};
+    const cuuint64_t gstr[4] = {n * 4, n * M * 4, n * M * W * 4, n * M * W * H * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)(2 * P), 1u, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, (cuuint32_t)R};
+    if (int e = encode(&maps[1], loc, 5, gdim, gstr, box)) return e;
+  }
+  {  // attn / logits [B*R][H][W][M][L*P]
+    const cuuint64_t n = u * L * P;
+    const cuuint64_t gdim[5] = {n, u * M, u * W, u * H, u * B * R};
+    const cuuint64_t gstr[4] = {n * 4, n * M * 4, n * M * W * 4, n * M * W * H * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)P, 1u, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, (cuuint32_t)R};
+    if (int e = encode(&maps[2], attn, 5, gdim, gstr, box)) return e;
+  }
+  if (FUSED) {  // reference table, level-major [L][H][W*P*2]
+    const cuuint64_t n = u * W * P * 2;
+    const cuuint64_t gdim[3] = {n, u * H, u * L};
+    const cuuint64_t gstr[2] = {n * 4, n * H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)(pl.TW * P * 2), (cuuint32_t)pl.TH, 1u};
+    if (int e = encode(&maps[3], ref, 3, gdim, gstr, box)) return e;
+  } else {
+    maps[3] = maps[2];
+  }
+
   VgParams prm;
   prm.value = value;
-  prm.loc = loc;
-  prm.attn = attn;
-  prm.ref = ref;
   prm.out = out;
-  prm.attn_out = attn_out;
-  prm.loc_out = loc_out;
+  prm.off_bias = off_bias;
+  prm.logit_bias = logit_bias;
   prm.H = H;
   prm.W = W;
   prm.M = M;
   prm.L = L;
   prm.R = R;
-  prm.Lr = Lr > 0 ? Lr : 1;
   prm.TH = pl.TH;
   prm.TW = pl.TW;
   prm.tiles_x = pl.tiles_x;
   prm.BW = pl.BW;
   prm.BH = pl.BH;
+  prm.off_a = pl.off_a;
+  prm.off_b = pl.off_b;
+  prm.off_ref = pl.off_ref;
+  prm.stage_bytes = pl.stage_bytes;
+  prm.zero_off = pl.zero_off;
+  prm.zero_bytes = pl.zero_bytes;
+  prm.tx_bytes = pl.tx_bytes;
+  const int tiles = pl.tiles_x * pl.tiles_y;
 #define MVD_VG(DD, PP) \
-  if (D == DD && P == PP) return launch_viewgrid<DD, PP, FUSED>(map, prm, pl, B, st)
+  if (D == DD && P == PP) return launch_vg<DD, PP, FUSED>(maps, prm, pl, tiles, B, st)
   MVD_VG(8, 4);
   MVD_VG(16, 4);
   MVD_VG(32, 4);
@@ -450,6 +537,7 @@ static int viewgrid_dispatch(const float* value, const float* loc, const float* 
   return MVD_ERR_UNSUPPORTED;
 }
 
+}  // namespace
 }  // namespace mvd
 
 using namespace mvd;
@@ -457,17 +545,17 @@ using namespace mvd;
 extern "C" int mvd_msda_fwd_viewgrid_f32(const float* value, const float* loc, const float* attn, int B, int H,
                                          int W, int M, int D, int L, int R, int P, float* out, void* stream) {
   if (!value || !loc || !attn || !out) return MVD_ERR_NULL_POINTER;
-  return viewgrid_dispatch<false>(value, loc, attn, nullptr, B, H, W, M, D, L, R, P, 1, out, nullptr, nullptr,
-                                  (cudaStream_t)stream);
+  return viewgrid_dispatch<false>(value, loc, attn, nullptr, nullptr, nullptr, B, H, W, M, D, L, R, P, 1, out, (cudaStream_t)stream);
 }
 
 extern "C" int mvd_msda_fused_fwd_viewgrid_f32(const float* value, const float* offsets, const float* logits,
-                                               const float* ref, int B, int H, int W, int M, int D, int L, int R,
-                                               int P, int Lr, float* out, float* attn_out, float* loc_out,
+                                               const float* ref, const float* off_bias,
+                                               const float* logit_bias, int B, int H, int W, int M, int D, int L,
+                                               int R, int P, int Lr, float* out, float* attn_out, float* loc_out,
                                                void* stream) {
   if (!value || !offsets || !logits || !ref || !out) return MVD_ERR_NULL_POINTER;
   if (Lr <= 0) return MVD_ERR_BAD_SHAPE;
   if (attn_out || loc_out) return MVD_ERR_UNSUPPORTED;  // normalisation is deferred here; the generic kernel writes them
-  return viewgrid_dispatch<true>(value, offsets, logits, ref, B, H, W, M, D, L, R, P, Lr, out, attn_out, loc_out,
+  return viewgrid_dispatch<true>(value, offsets, logits, ref, off_bias, logit_bias, B, H, W, M, D, L, R, P, Lr, out,
                                  (cudaStream_t)stream);
 }

@@ -22,6 +22,7 @@ from torch.autograd.function import once_differentiable
 from . import _C
 
 _VIEWGRID = os.environ.get("MVDETR_B200_VIEWGRID", "1") != "0"
+_WARP_CL = os.environ.get("MVDETR_B200_WARP_CL", "1") != "0"  # 0: always the scalar NCHW-source warp kernels (A/B switch)
 
 
 def _stream(t):
@@ -188,14 +189,16 @@ def msda_viewgrid_forward(value, sampling_loc, attn_weight, H, W):
 
 
 def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits, ref_table, want_aux=False,
-                       grid_hw=None, ref_table_lm=None):
+                       grid_hw=None, ref_table_lm=None, off_bias=None, logit_bias=None):
     """out = MSDA(value, loc = ref + offsets/(W_l,H_l), attn = softmax(logits)) in one kernel (inference path).
 
     value [B,S,M,D] fp32; offsets [B,Lq,M,L,P,2] and logits [B,Lq,M,L*P]: raw Linear outputs; ref_table [Lr,L,P,2]
     (query q reads row q % Lr). Returns out [B,Lq,M*D], plus (attn, loc) when want_aux.
     grid_hw=(H, W) (host ints) asserts the MVDeTr encoder layout -- every level an HxW grid, S = L*H*W, Lq = R*H*W --
     and selects the TMA-staged view-grid kernel; the generic kernel is used when that layout has no instantiation.
-    ref_table_lm: optional precomputed level-major copy of ref_table, [L,Lr,P,2] (made on the fly when None)."""
+    ref_table_lm: optional precomputed level-major copy of ref_table, [L,Lr,P,2] (made on the fly when None).
+    off_bias [M*L*P*2] / logit_bias [M*L*P]: optional biases of the two Linear layers, added in the kernel so the
+    caller can run both as bias-free GEMMs (cuBLASLt applies an fp32 bias in a separate pass over the output)."""
     B, S, M, D = value.shape
     _, Lq, _, L, P, _ = offsets.shape
     for name, t in (("value", value), ("offsets", offsets), ("logits", logits), ("ref_table", ref_table)):
@@ -203,6 +206,11 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
             raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor")
     if logits.numel() != B * Lq * M * L * P or tuple(ref_table.shape[1:]) != (L, P, 2):
         raise RuntimeError("msda_fused_forward: inconsistent shapes")
+    for name, t, n in (("off_bias", off_bias, M * L * P * 2), ("logit_bias", logit_bias, M * L * P)):
+        if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and t.numel() == n):
+            raise RuntimeError(f"msda_fused_forward: {name} must be a contiguous fp32 CUDA tensor of {n} elements")
+    ob = off_bias.data_ptr() if off_bias is not None else None
+    lb = logit_bias.data_ptr() if logit_bias is not None else None
     out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
     attn = torch.empty((B, Lq, M, L, P), dtype=value.dtype, device=value.device) if want_aux else None
     loc = torch.empty_like(offsets) if want_aux else None
@@ -217,7 +225,8 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
             elif tuple(ref_table_lm.shape) != (L, ref_table.shape[0], P, 2) or not ref_table_lm.is_contiguous():
                 raise RuntimeError("msda_fused_forward: ref_table_lm must be contiguous [L, Lr, P, 2]")
             rc = _C.lib.mvd_msda_fused_fwd_viewgrid_f32(value.data_ptr(), offsets.data_ptr(), logits.data_ptr(),
-                                                        ref_table_lm.data_ptr(), B, H, W, M, D, L, Lq // (H * W), P,
+                                                        ref_table_lm.data_ptr(), ob, lb, B, H, W, M, D, L,
+                                                        Lq // (H * W), P,
                                                         ref_table.shape[0], out.data_ptr(), None, None,
                                                         _stream(value))
             if rc == 0:
@@ -225,17 +234,18 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
             if rc != -3:  # MVD_ERR_UNSUPPORTED -> generic kernel
                 _C.check(rc, "mvd_msda_fused_fwd_viewgrid_f32")
         rc = _C.lib.mvd_msda_fused_fwd_f32(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-                                           offsets.data_ptr(), logits.data_ptr(), ref_table.data_ptr(), B, S, M, D, L,
-                                           Lq, P, ref_table.shape[0], out.data_ptr(), *aux, _stream(value))
+                                           offsets.data_ptr(), logits.data_ptr(), ref_table.data_ptr(), ob, lb, B, S,
+                                           M, D, L, Lq, P, ref_table.shape[0], out.data_ptr(), *aux, _stream(value))
     _C.check(rc, "mvd_msda_fused_fwd_f32")
     return (out, attn, loc) if want_aux else out
 
 
-def add_layer_norm(x, res, weight, bias, eps=1e-5):
-    """LayerNorm(x + res) over the last dim in one kernel (inference glue of the encoder layer,
-    ref: multiview_detector/models/deformable_transformer.py:79-80,84-85). res may be None."""
+def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None):
+    """LayerNorm(x + (res + res_bias)) over the last dim in one kernel (inference glue of the encoder layer,
+    ref: multiview_detector/models/deformable_transformer.py:79-80,84-85). res may be None; res_bias [C] is the bias
+    of the Linear that produced `res` when that GEMM was run bias-free."""
     C = x.shape[-1]
-    for name, t in (("x", x), ("res", res), ("weight", weight), ("bias", bias)):
+    for name, t in (("x", x), ("res", res), ("weight", weight), ("bias", bias), ("res_bias", res_bias)):
         if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
             raise RuntimeError(f"add_layer_norm: {name} must be a contiguous fp32 CUDA tensor")
     if res is not None and res.shape != x.shape:
@@ -243,31 +253,74 @@ def add_layer_norm(x, res, weight, bias, eps=1e-5):
     out = torch.empty_like(x)
     with _on_device(x):
         rc = _C.lib.mvd_add_layernorm_f32(x.data_ptr(), res.data_ptr() if res is not None else None,
-                                          weight.data_ptr(), bias.data_ptr(), x.numel() // C, C, float(eps),
+                                          res_bias.data_ptr() if res_bias is not None else None, weight.data_ptr(), bias.data_ptr(), x.numel() // C, C, float(eps),
                                           out.data_ptr(), _stream(x))
     _C.check(rc, "mvd_add_layernorm_f32")
     return out
 
 
+_DST_NHWC, _SRC_NHWC = 1, 2  # MVD_WARP_* layout bits of include/mvdetr_b200.h
+
+
+def transpose_last2(x):
+    """[batch, rows, cols] fp32 CUDA contiguous -> [batch, cols, rows] contiguous (mvd_transpose_f32): the NCHW <-> NHWC
+    relayout kernel."""
+    batch, rows, cols = x.shape
+    out = torch.empty((batch, cols, rows), dtype=x.dtype, device=x.device)
+    with _on_device(x):
+        rc = _C.lib.mvd_transpose_f32(x.data_ptr(), batch, rows, cols, out.data_ptr(), _stream(x))
+    _C.check(rc, "mvd_transpose_f32")
+    return out
+
+
+def _as_nhwc(x):
+    """NCHW-shaped fp32 CUDA tensor -> (tensor whose storage is [N,H,W,C] contiguous, made_copy)."""
+    N, C, H, W = x.shape
+    if x.is_contiguous(memory_format=torch.channels_last) and not (C == 1 or H * W == 1):
+        return x.permute(0, 2, 3, 1), False
+    x = x.contiguous()
+    return transpose_last2(x.view(N, C, H * W)).view(N, H, W, C), True
+
+
 class _WarpPerspective(Function):
+    """Layout policy: with C % 4 == 0 the gather runs on a channels-last source (every tap one contiguous C-vector).
+    A torch channels_last input is used in place; a plain NCHW input is relaid out once by mvd_transpose_f32
+    (51.6 MB read + write at Wildtrack size, cheaper than gathering scalars from C planes). Other C take the
+    scalar NCHW kernels."""
+
     @staticmethod
     def forward(ctx, src, mat, Ho, Wo, channels_last):
         BN, C, Hi, Wi = src.shape
         shape = (BN, Ho, Wo, C) if channels_last else (BN, C, Ho, Wo)
         dst = torch.empty(shape, dtype=src.dtype, device=src.device)
+        vec = C % 4 == 0 and _WARP_CL
+        layout = _DST_NHWC if channels_last else 0
+        if vec:
+            src, _ = _as_nhwc(src)
+            layout |= _SRC_NHWC
+        else:
+            src = src.contiguous()
         with _on_device(src):
             rc = _C.lib.mvd_warp_fwd_f32(src.data_ptr(), mat.data_ptr(), BN, C, Hi, Wi, Ho, Wo, dst.data_ptr(),
-                                         1 if channels_last else 0, _stream(src))
+                                         layout, _stream(src))
         _C.check(rc, "mvd_warp_fwd_f32")
         ctx.save_for_backward(mat)
-        ctx.geom = (BN, C, Hi, Wi, Ho, Wo, channels_last)
+        ctx.geom = (BN, C, Hi, Wi, Ho, Wo, channels_last, vec)
         return dst
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_dst):
         (mat,) = ctx.saved_tensors
-        BN, C, Hi, Wi, Ho, Wo, channels_last = ctx.geom
+        BN, C, Hi, Wi, Ho, Wo, channels_last, vec = ctx.geom
+        if vec:
+            g_cl = grad_dst.contiguous() if channels_last else _as_nhwc(grad_dst)[0]
+            grad_src = torch.empty((BN, Hi, Wi, C), dtype=grad_dst.dtype, device=grad_dst.device)
+            with _on_device(grad_dst):
+                rc = _C.lib.mvd_warp_bwd_nhwc_f32(g_cl.data_ptr(), mat.data_ptr(), BN, C, Hi, Wi, Ho, Wo,
+                                                  grad_src.data_ptr(), _stream(grad_dst))
+            _C.check(rc, "mvd_warp_bwd_nhwc_f32")
+            return grad_src.permute(0, 3, 1, 2), None, None, None, None  # NCHW-shaped view, channels_last strides
         if channels_last:
             grad_dst = grad_dst.permute(0, 3, 1, 2)
         grad_dst = grad_dst.contiguous()
@@ -301,4 +354,4 @@ def warp_perspective(src, M, dsize, mode="bilinear", padding_mode="zeros", align
         raise RuntimeError(f"mvdetr_b200.warp_perspective: fp32 only, got {src.dtype}")
     Ho, Wo = int(dsize[0]), int(dsize[1])
     mat = M.detach().to(device=src.device, dtype=torch.float32).contiguous()
-    return _WarpPerspective.apply(src.contiguous(), mat, Ho, Wo, bool(channels_last))
+    return _WarpPerspective.apply(src, mat, Ho, Wo, bool(channels_last))

@@ -124,15 +124,19 @@ class ShardedFusion:
             value = gather_rows(mine, part, hw, rank, out=gbuf, group=self.group)
             if nq:
                 query = src + pos
-                offsets = attn.sampling_offsets(query).view(1, nq, M, L, P, 2)
-                logits = attn.attention_weights(query).view(1, nq, M, L * P)
+                # bias-free GEMMs; the biases are applied inside our kernels (see world_feat.MSDeformAttn.forward)
+                offsets = torch.mm(query, attn.sampling_offsets.weight.t()).view(1, nq, M, L, P, 2)
+                logits = torch.mm(query, attn.attention_weights.weight.t()).view(1, nq, M, L * P)
                 out = ops.msda_fused_forward(value.view(1, S, M, C // M), geo.shapes, geo.start, offsets, logits,
-                                             table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm)
-                src2 = attn.output_proj(out.view(nq, C))
-                src = ops.add_layer_norm(src, src2, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+                                             table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm,
+                                             off_bias=attn.sampling_offsets.bias, logit_bias=attn.attention_weights.bias)
+                src2 = torch.mm(out.view(nq, C), attn.output_proj.weight.t())
+                src = ops.add_layer_norm(src, src2, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps,
+                                         res_bias=attn.output_proj.bias)
                 hidden = torch._addmm_activation(layer.linear1.bias, src, layer.linear1.weight.t())
-                src2 = layer.linear2(hidden)
-                src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+                src2 = torch.mm(hidden, layer.linear2.weight.t())
+                src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
+                                         res_bias=layer.linear2.bias)
         memory = gather_rows(src, part, hw, rank, out=gbuf, group=self.group)
         merged = wf.merge_linear(memory.view(1, N, Hd, Wd, C).permute(0, 1, 4, 2, 3).reshape(1, N * C, Hd, Wd))
         return wf.upsample(merged)

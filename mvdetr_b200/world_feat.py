@@ -95,10 +95,11 @@ class MSDeformAttn(nn.Module):
         constant_(self.output_proj.bias.data, 0.)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, geometry=None, ref_table=None, ref_table_lm=None):
+                input_padding_mask=None, geometry=None, ref_table=None, ref_table_lm=None, defer_output_bias=False):
         """Reference signature (first six arguments). Extensions used by our encoder: `geometry` (LevelGeometry,
-        avoids the device->host check) and `ref_table` ([Lr,L,P,2] compact reference points: enables the fused
-        kernel when autograd is off)."""
+        avoids the device->host check), `ref_table` ([Lr,L,P,2] compact reference points: enables the fused
+        kernel when autograd is off) and `defer_output_bias` (fused path only: returns output_proj WITHOUT its bias,
+        which the caller adds inside the residual+LayerNorm kernel)."""
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
         if geometry is not None:
@@ -111,18 +112,27 @@ class MSDeformAttn(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, M, self.d_model // M)
-        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
-        attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
 
         fused = (ref_table is not None and not torch.is_grad_enabled() and value.dtype == torch.float32 and
                  value.is_cuda)
+        assert fused or not defer_output_bias, "defer_output_bias is only valid on the fused inference path"
         if fused:
+            # both Linear layers as bias-free GEMMs (cuBLASLt runs an fp32 bias as a separate pass over the 135 MB /
+            # 68 MB outputs); the biases are added inside the kernel before the same arithmetic as the reference
+            q2 = query.reshape(N * Len_q, -1)
+            sampling_offsets = torch.mm(q2, self.sampling_offsets.weight.t()).view(N, Len_q, M, L, P, 2)
+            attention_weights = torch.mm(q2, self.attention_weights.weight.t()).view(N, Len_q, M, L * P)
             grid_hw = geometry.hw[0] if geometry is not None and geometry.uniform else None
             output = ops.msda_fused_forward(value.contiguous(), input_spatial_shapes, input_level_start_index,
-                                            sampling_offsets.contiguous(), attention_weights.contiguous(), ref_table,
-                                            grid_hw=grid_hw, ref_table_lm=ref_table_lm)
+                                            sampling_offsets, attention_weights, ref_table,
+                                            grid_hw=grid_hw, ref_table_lm=ref_table_lm,
+                                            off_bias=self.sampling_offsets.bias, logit_bias=self.attention_weights.bias)
+            if defer_output_bias:
+                return torch.mm(output.view(N * Len_q, -1), self.output_proj.weight.t()).view(N, Len_q, -1)
             return self.output_proj(output)
 
+        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
+        attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
         if reference_points.shape[-1] != 2:
             raise ValueError("Last dim of reference_points must be 2, but get {} instead.".format(
@@ -156,17 +166,21 @@ class DeformableTransformerEncoderLayer(nn.Module):
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
                 geometry=None, ref_table=None, ref_table_lm=None):
+        fast = (not torch.is_grad_enabled() and not self.training and src.is_cuda and src.dtype == torch.float32
+                and src.shape[-1] % 4 == 0 and src.shape[-1] <= 1024)
+        defer = fast and ref_table is not None
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                               level_start_index, padding_mask, geometry=geometry, ref_table=ref_table,
-                              ref_table_lm=ref_table_lm)
-        if (not torch.is_grad_enabled() and not self.training and src.is_cuda and src.dtype == torch.float32
-                and src.shape[-1] % 4 == 0 and src.shape[-1] <= 1024):
-            # inference: residual+LayerNorm in one kernel, bias+ReLU in the GEMM epilogue; same arithmetic
+                              ref_table_lm=ref_table_lm, defer_output_bias=defer)
+        if fast:
+            # inference: residual (+ deferred Linear bias) + LayerNorm in one kernel, bias+ReLU in the GEMM epilogue,
+            # linear2 bias-free with its bias folded into the second LayerNorm kernel; same arithmetic
             src = ops.add_layer_norm(src.contiguous(), src2.contiguous(), self.norm1.weight, self.norm1.bias,
-                                     self.norm1.eps)
+                                     self.norm1.eps, res_bias=self.self_attn.output_proj.bias if defer else None)
             hidden = torch._addmm_activation(self.linear1.bias, src.view(-1, src.shape[-1]), self.linear1.weight.t())
-            src2 = self.linear2(hidden).view(src.shape)
-            return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+            src2 = torch.mm(hidden, self.linear2.weight.t()).view(src.shape)
+            return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                      res_bias=self.linear2.bias)
         src = self.norm1(src + self.dropout1(src2))
         src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
         return self.norm2(src + self.dropout3(src2))

@@ -267,3 +267,43 @@ def test_viewgrid_fused_matches_unfused_and_generic(cuda):
     sub = ops.msda_fused_forward(value, shapes, start, offsets[:, 2 * hw:5 * hw].contiguous(),
                                  logits[:, 2 * hw:5 * hw].contiguous(), table, grid_hw=(H, W))
     assert torch.equal(sub, o_vg[:, 2 * hw:5 * hw])
+
+
+@pytest.mark.parametrize("grid", [True, False])
+def test_fused_bias_folding_is_bit_identical(cuda, grid):
+    """off_bias / logit_bias added inside the kernel == the same biases added by the Linear layers beforehand
+    (fl(raw + bias) either way), for the view-grid and the generic fused kernel."""
+    L, H, W, M, D, P = 5, 12, 20, 4, 16, 4
+    g = torch.Generator().manual_seed(123)
+    S = Lq = L * H * W
+    value = torch.randn(1, S, M, D, generator=g).to(cuda)
+    raw_off = (torch.randn(1, Lq, M, L, P, 2, generator=g) * 2).to(cuda)
+    raw_log = torch.randn(1, Lq, M, L * P, generator=g).to(cuda)
+    off_bias = (torch.randn(M * L * P * 2, generator=g) * 3).to(cuda)
+    logit_bias = torch.randn(M * L * P, generator=g).to(cuda)
+    ys, xs = torch.meshgrid(torch.linspace(0.5, H - 0.5, H), torch.linspace(0.5, W - 0.5, W), indexing="ij")
+    table = torch.stack((xs / W, ys / H), -1).reshape(H * W, 1, 1, 2).repeat(1, L, P, 1).contiguous().to(cuda)
+    shapes = torch.as_tensor([[H, W]] * L, dtype=torch.long, device=cuda)
+    start = torch.arange(L, device=cuda) * (H * W)
+    kw = dict(grid_hw=(H, W)) if grid else {}
+    pre = ops.msda_fused_forward(value, shapes, start, raw_off + off_bias.view(1, 1, M, L, P, 2),
+                                 raw_log + logit_bias.view(1, 1, M, L * P), table, **kw)
+    folded = ops.msda_fused_forward(value, shapes, start, raw_off, raw_log, table, off_bias=off_bias,
+                                    logit_bias=logit_bias, **kw)
+    assert torch.equal(pre, folded)
+    _, attn, loc = ops.msda_fused_forward(value, shapes, start, raw_off, raw_log, table, want_aux=True,
+                                          off_bias=off_bias, logit_bias=logit_bias)
+    ref = co.msda_forward(value.cpu().numpy(), shapes.cpu().numpy(), start.cpu().numpy(), loc.cpu().numpy(),
+                          attn.cpu().numpy())
+    assert np.abs(folded.cpu().numpy() - ref).max() <= FP32_ATOL
+
+
+@pytest.mark.parametrize("C", [128, 256, 64])
+def test_add_layer_norm_with_deferred_bias(cuda, C):
+    g = torch.Generator().manual_seed(C)
+    x, res = torch.randn(1000, C, generator=g).to(cuda), torch.randn(1000, C, generator=g).to(cuda)
+    w, b, rb = (torch.randn(C, generator=g).to(cuda) for _ in range(3))
+    want = torch.nn.functional.layer_norm(x + (res + rb), (C,), w, b, 1e-5)
+    got = ops.add_layer_norm(x, res, w, b, 1e-5, res_bias=rb)
+    assert (got - want).abs().max().item() <= 2e-5
+    assert torch.equal(ops.add_layer_norm(x, res + rb, w, b, 1e-5), got)

@@ -92,3 +92,69 @@ def test_host_buffer_entry_point(cuda):
     assert rc == 0, _C.error_string(rc)
     out = ops.warp_perspective(src.to(cuda), mats.to(cuda), (12, 20), align_corners=False)
     assert torch.equal(out.cpu(), out_host)
+
+
+@pytest.mark.parametrize("C,Hi,Wi,Ho,Wo", [(128, 18, 32, 24, 72), (8, 9, 16, 15, 33), (132, 7, 5, 3, 11), (256, 12, 20, 10, 30)])
+def test_every_layout_gives_the_same_values(cuda, C, Hi, Wi, Ho, Wo):
+    """NCHW / channels_last source x NCHW / channels-last destination: the vector (channels-last source) kernels, the
+    scalar NCHW kernels and the C oracle agree; a torch channels_last input is consumed in place."""
+    rng = np.random.RandomState(C + Ho)
+    src = rng.randn(3, C, Hi, Wi).astype(np.float32)
+    mats = _ring_homographies(3, Hi, Wi, Ho, Wo, seed=C)
+    ref = co.warp_forward(src, mats, (Ho, Wo))
+    d_src, d_mats = dev(src, cuda), dev(mats, cuda)
+    outs = {}
+    for name, s in (("nchw", d_src), ("cl", d_src.contiguous(memory_format=torch.channels_last))):
+        for cl_out in (False, True):
+            o = ops.warp_perspective(s, d_mats, (Ho, Wo), align_corners=False, channels_last=cl_out)
+            outs[(name, cl_out)] = o.permute(0, 3, 1, 2) if cl_out else o
+    old = ops._WARP_CL
+    try:
+        ops._WARP_CL = False  # scalar kernels reading the NCHW source directly
+        outs[("scalar", False)] = ops.warp_perspective(d_src, d_mats, (Ho, Wo), align_corners=False)
+        outs[("scalar", True)] = ops.warp_perspective(d_src, d_mats, (Ho, Wo), align_corners=False,
+                                                      channels_last=True).permute(0, 3, 1, 2)
+    finally:
+        ops._WARP_CL = old
+    base = outs[("nchw", False)]
+    assert np.abs(base.cpu().numpy() - ref).max() <= ATOL
+    for key, o in outs.items():
+        assert o.shape == base.shape, key
+        assert (o - base).abs().max().item() <= 1e-6, key
+
+
+def test_channels_last_backward_is_the_adjoint(cuda):
+    """Vector backward (red.global.add.v4) against the scalar-atomics backward and the adjoint identity, for both
+    gradient layouts autograd can hand over."""
+    BN, C, Hi, Wi, Ho, Wo = 2, 64, 14, 22, 19, 37
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(BN, C, Hi, Wi, generator=g).to(cuda)
+    mats = torch.from_numpy(_ring_homographies(BN, Hi, Wi, Ho, Wo, seed=9)).to(cuda)
+    gout = torch.randn(BN, C, Ho, Wo, generator=g).to(cuda)
+    grads = []
+    for flag, go in ((True, gout), (True, gout.contiguous(memory_format=torch.channels_last)), (False, gout)):
+        old = ops._WARP_CL
+        try:
+            ops._WARP_CL = flag
+            s = src.clone().requires_grad_(True)
+            out = ops.warp_perspective(s, mats, (Ho, Wo), align_corners=False)
+            out.backward(go)
+        finally:
+            ops._WARP_CL = old
+        grads.append(s.grad)
+        lhs, rhs = (out.detach() * gout).sum().item(), (src * s.grad).sum().item()
+        assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(lhs))
+    assert grads[0].shape == src.shape
+    for gr in grads[:2]:
+        assert (gr - grads[2]).abs().max().item() <= 1e-4 * max(1.0, grads[2].abs().max().item())
+    # channels-last OUTPUT: gradient arrives as [BN, Ho, Wo, C]
+    s = src.clone().requires_grad_(True)
+    ops.warp_perspective(s, mats, (Ho, Wo), align_corners=False, channels_last=True).backward(
+        gout.permute(0, 2, 3, 1).contiguous())
+    assert (s.grad - grads[2]).abs().max().item() <= 1e-4 * max(1.0, grads[2].abs().max().item())
+
+
+@pytest.mark.parametrize("batch,rows,cols", [(1, 1, 1), (3, 37, 65), (2, 128, 14400), (1, 33, 32)])
+def test_transpose_kernel(cuda, batch, rows, cols):
+    x = torch.randn(batch, rows, cols, generator=torch.Generator().manual_seed(rows)).to(cuda)
+    assert torch.equal(ops.transpose_last2(x), x.transpose(1, 2).contiguous())
