@@ -197,6 +197,12 @@ MVD_API int mvd_transpose_f32(const float* in, int batch, int rows, int cols, fl
 MVD_API int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma, const float* beta,
                                   int64_t rows, int C, float eps, float* out, void* stream);
 
+/* In-place x[r, c] = act(x[r, c] + bias[c]) over [rows, C] (C % 4 == 0, 16-byte aligned), act = ReLU when `relu` != 0:
+ * the bias (+ReLU) of a Linear layer whose GEMM ran bias-free.
+ *   replaces the bias/activation of `self.linear1` + F.relu  ref: mvd/models/deformable_transformer.py:82
+ *   and of `value_proj`                                       ref: mvd/models/ops/modules/ms_deform_attn.py:96 */
+MVD_API int mvd_bias_act_f32(float* x, const float* bias, int64_t rows, int C, int relu, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (used for end-to-end timing and by non-PyTorch callers):
  * same arguments, but every pointer is HOST memory (pinned or pageable). They allocate device

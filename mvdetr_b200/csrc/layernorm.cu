@@ -73,9 +73,41 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   }
 }
 
+// In-place x[r, c] = act(x[r, c] + bias[c]) for the output of a bias-free GEMM (act = ReLU or identity). cuBLASLt
+// applies an fp32 bias/ReLU epilogue of its SIMT kernels as a separate scalar pass (profiles/r01a_launches.csv:
+// `cublasLt::globalKernel`, 175 us for the [75600, 512] FFN hidden at 1.8 TB/s); this is the same pass with 128-bit
+// accesses.   ref: multiview_detector/models/deformable_transformer.py:82 (linear1 + ReLU), ms_deform_attn.py:96
+template <bool RELU>
+__global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict__ x, const float* __restrict__ bias,
+                                                       int64_t n4, int C4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % C4));
+    v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+    if (RELU) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+}
+
 }  // namespace mvd
 
 using namespace mvd;
+
+extern "C" int mvd_bias_act_f32(float* x, const float* bias, int64_t rows, int C, int relu, void* stream) {
+  if (!x || !bias) return MVD_ERR_NULL_POINTER;
+  if (rows <= 0 || C <= 0) return MVD_ERR_BAD_SHAPE;
+  if (C & 3) return MVD_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(bias)) & 15u) return MVD_ERR_MISALIGNED;
+  const int64_t n4 = rows * (C / 4);
+  const int64_t want = ceil_div64(n4, 256);
+  const int blocks = (int)(want > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : want);
+  if (relu)
+    bias_act_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, n4, C / 4);
+  else
+    bias_act_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, bias, n4, C / 4);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
 
 extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma,
                                      const float* beta,

@@ -282,6 +282,20 @@ def _as_nhwc(x):
     return transpose_last2(x.view(N, C, H * W)).view(N, H, W, C), True
 
 
+def bias_act_(x, bias, relu=False):
+    """In place: x = act(x + bias) over the last dim (mvd_bias_act_f32); x is the output of a bias-free GEMM."""
+    C = x.shape[-1]
+    for name, t in (("x", x), ("bias", bias)):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError(f"bias_act_: {name} must be a contiguous fp32 CUDA tensor")
+    if bias.numel() != C:
+        raise RuntimeError("bias_act_: bias must have one entry per column")
+    with _on_device(x):
+        rc = _C.lib.mvd_bias_act_f32(x.data_ptr(), bias.data_ptr(), x.numel() // C, C, 1 if relu else 0, _stream(x))
+    _C.check(rc, "mvd_bias_act_f32")
+    return x
+
+
 class _WarpPerspective(Function):
     """Layout policy: with C % 4 == 0 the gather runs on a channels-last source (every tap one contiguous C-vector).
     A torch channels_last input is used in place; a plain NCHW input is relaid out once by mvd_transpose_f32

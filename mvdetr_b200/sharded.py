@@ -133,7 +133,7 @@ class ShardedFusion:
                 src2 = torch.mm(out.view(nq, C), attn.output_proj.weight.t())
                 src = ops.add_layer_norm(src, src2, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps,
                                          res_bias=attn.output_proj.bias)
-                hidden = torch._addmm_activation(layer.linear1.bias, src, layer.linear1.weight.t())
+                hidden = ops.bias_act_(torch.mm(src, layer.linear1.weight.t()), layer.linear1.bias, relu=True)
                 src2 = torch.mm(hidden, layer.linear2.weight.t())
                 src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
                                          res_bias=layer.linear2.bias)

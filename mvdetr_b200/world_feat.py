@@ -108,13 +108,16 @@ class MSDeformAttn(nn.Module):
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
-        value = self.value_proj(input_flatten)
+        fused = (ref_table is not None and not torch.is_grad_enabled() and input_flatten.dtype == torch.float32 and
+                 input_flatten.is_cuda)
+        if fused and self.d_model % 4 == 0:
+            value = ops.bias_act_(torch.mm(input_flatten.reshape(N * Len_in, -1), self.value_proj.weight.t()),
+                                  self.value_proj.bias)
+        else:
+            value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, M, self.d_model // M)
-
-        fused = (ref_table is not None and not torch.is_grad_enabled() and value.dtype == torch.float32 and
-                 value.is_cuda)
         assert fused or not defer_output_bias, "defer_output_bias is only valid on the fused inference path"
         if fused:
             # both Linear layers as bias-free GEMMs (cuBLASLt runs an fp32 bias as a separate pass over the 135 MB /
@@ -177,7 +180,8 @@ class DeformableTransformerEncoderLayer(nn.Module):
             # linear2 bias-free with its bias folded into the second LayerNorm kernel; same arithmetic
             src = ops.add_layer_norm(src.contiguous(), src2.contiguous(), self.norm1.weight, self.norm1.bias,
                                      self.norm1.eps, res_bias=self.self_attn.output_proj.bias if defer else None)
-            hidden = torch._addmm_activation(self.linear1.bias, src.view(-1, src.shape[-1]), self.linear1.weight.t())
+            hidden = ops.bias_act_(torch.mm(src.view(-1, src.shape[-1]), self.linear1.weight.t()), self.linear1.bias,
+                                   relu=True)
             src2 = torch.mm(hidden, self.linear2.weight.t()).view(src.shape)
             return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps,
                                       res_bias=self.linear2.bias)

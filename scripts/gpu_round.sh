@@ -10,6 +10,6 @@ echo "== pytest -m gpu" ; timeout 1200 python -m pytest tests -m gpu -x -q > $OU
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/${TAG}_smoke.log
 echo "== bench ours" ; timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
 echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "ref rc=$?"; cat $OUT/${TAG}_bench_ref.json
-echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
-echo "== ncu full (msda + warp)" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:'msda_|warp_' -c 8 -f -o $OUT/${TAG}_prof python scripts/prof_kernels.py > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+echo "== ncu launch list" ; timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
+echo "== ncu full (msda + warp)" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:'msda_|warp_|transpose_' -c 14 -f -o $OUT/${TAG}_prof python scripts/prof_kernels.py > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT

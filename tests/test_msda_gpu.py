@@ -307,3 +307,12 @@ def test_add_layer_norm_with_deferred_bias(cuda, C):
     got = ops.add_layer_norm(x, res, w, b, 1e-5, res_bias=rb)
     assert (got - want).abs().max().item() <= 2e-5
     assert torch.equal(ops.add_layer_norm(x, res + rb, w, b, 1e-5), got)
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_bias_act_inplace(cuda, relu):
+    g = torch.Generator().manual_seed(7)
+    x, b = torch.randn(777, 512, generator=g).to(cuda), torch.randn(512, generator=g).to(cuda)
+    want = torch.relu(x + b) if relu else x + b
+    got = ops.bias_act_(x.clone(), b, relu=relu)
+    assert torch.equal(got, want)
