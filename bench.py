@@ -333,7 +333,13 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cudnn.benchmark = True  # as the reference sets it (main.py:48); tuned before graph capture
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        import threading
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
+        # hard watchdog: a wedged collective must end the process (non-zero), never hang the box
+        wd = threading.Timer(600.0, lambda: (log("bench.py: watchdog fired, aborting"), os._exit(3)))
+        wd.daemon = True
+        wd.start()
 
     from mvdetr_b200.fusion import FrameRunner
     ds, fusion = build_fusion(device)
@@ -354,9 +360,12 @@ def run_ours(args):
     out_shape = (1, HIDDEN, *ds.Rworld_shape)
 
     def barrier():
+        # drain this rank's streams BEFORE the collective: the graph replays on runner.compute contain all-gathers on
+        # the same communicator, and a barrier kernel racing them on another stream can order differently per rank
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`): inputs already in HBM, alternate the two slots ----
     for s in range(runner.depth):
