@@ -26,7 +26,9 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     ok = True
-    for name, make in (("wildtrack", synthetic.wildtrack_like), ("multiviewx", synthetic.multiviewx_like)):
+    # the one-view scene leaves every rank but the first WITHOUT views (the 8-GPU run of a 7-view scene has one such rank)
+    for name, make in (("wildtrack", synthetic.wildtrack_like), ("multiviewx", synthetic.multiviewx_like),
+                       ("one_view", lambda seed: synthetic.mini_scene(num_cam=1, seed=seed))):
         torch.manual_seed(0)
         ds = make(seed=0)
         fusion = MultiviewFusion(ds, base_dim=128, hidden_dim=128, nhead=8, n_points=4)
