@@ -340,6 +340,9 @@ def run_ours(args):
         wd = threading.Timer(600.0, lambda: (log("bench.py: watchdog fired, aborting"), os._exit(3)))
         wd.daemon = True
         wd.start()
+        if os.environ.get("MVD_BENCH_TRACE"):  # debugging aid: dump every thread's Python stack if we stall
+            import faulthandler
+            faulthandler.dump_traceback_later(float(os.environ["MVD_BENCH_TRACE"]), exit=True, file=sys.stderr)
 
     from mvdetr_b200.fusion import FrameRunner
     ds, fusion = build_fusion(device)
@@ -367,6 +370,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    log(f"[rank {rank}] runner ready: mode={mode}")
     # ---- device-resident throughput (`value`): inputs already in HBM, alternate the two slots ----
     for s in range(runner.depth):
         runner.load(feats_dev[s % n_frames], projs_dev[s % n_frames], slot=s)
@@ -391,6 +395,7 @@ def run_ours(args):
         ms = t.item()
     clocks = sampler.stop() if sampler else None
     ms_per_step = ms / args.steps
+    log(f"[rank {rank}] timed region done: {ms_per_step:.3f} ms/step")
     frames_per_step = runner.frames_per_step if world > 1 else 1
     value = frames_per_step * 1e3 / ms_per_step
 
@@ -411,6 +416,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
     e2e_fps = frames_per_step * k / e2e_s
+    log(f"[rank {rank}] e2e done: {e2e_fps:.1f} frames/s")
     h2d = feats_pinned[0].numel() * 4 + BN * 36
     d2h = outs_pinned[0].numel() * 4
 
@@ -446,11 +452,18 @@ def run_ours(args):
                 "kernels": kb}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        # Tear down in the order NCCL needs: the captured graphs hold the communicator's kernels, and
+        # destroy_process_group() with live graphs never returns (seen on 2xB200: both ranks stuck in it).
+        dist.barrier()
+        runner.graphs = [None] * runner.depth
+        del runner
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 def main():
