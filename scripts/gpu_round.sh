@@ -13,3 +13,4 @@ echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps
 echo "== ncu launch list" ; timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
 echo "== ncu full (msda + warp)" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:'msda_|warp_|transpose_' -c 14 -f -o $OUT/${TAG}_prof python scripts/prof_kernels.py > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT
+echo "== sweep (configs 3/4)" ; timeout 900 python scripts/sweep.py --out $OUT/${TAG}_sweep.jsonl > $OUT/${TAG}_sweep.log 2>&1; echo "sweep rc=$?"; tail -3 $OUT/${TAG}_sweep.log | cut -c1-300
