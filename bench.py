@@ -421,6 +421,10 @@ def run_ours(args):
     d2h = outs_pinned[0].numel() * 4
 
     line = None
+    from mvdetr_b200 import ops as _ops
+    lt = _ops.linear_available()
+    gemm_mode = (f"{_ops._GEMM_MODE} via cuBLASLt {lt} (fp32 in/out; bf16x9 = CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32-accurate "
+                 f"tensor-core emulation)" if lt and _ops._GEMM_MODE != "torch" else "torch.mm fp32 (cuBLAS SIMT)")
     if rank == 0:
         kb = kernel_breakdown(fusion, ds, device)
         peak, peak_src = measured_peak_hbm()
@@ -439,12 +443,14 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "views": BN, "feat": list(feat_shape),
                            "world_grid": list(ds.Rworld_shape), "layers": LAYERS, "heads": HEADS, "points": POINTS,
                            "mode": mode, "cuda_graph": True, "tf32": False,
+                           "gemm": gemm_mode,
                            "l2": "2 alternating frame slots; per-step working set ~1.5 GB >> 126 MB L2"},
                 "roofline": roofline,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "pipeline": "pinned host -> H2D stream / graph replay / D2H stream, 2 slots"},
-                # ours per frame: transpose + warp, then per layer 2 bias_act + 1 fused MSDA + 2 add_layernorm
-                "gpu_launches": (2 + 5 * LAYERS) * args.steps,
+                # ours per frame: transpose + warp, then per layer 1 fused MSDA + 2 add_layernorm (+ 2 bias_act when the
+                # Linear layers run through torch.mm instead of the cuBLASLt epilogues)
+                "gpu_launches": (2 + (3 if lt and _ops._GEMM_MODE != "torch" else 5) * LAYERS) * args.steps,
                 "clocks": clocks,
                 "hot_path": {"warp_us": kb["warp"]["us"], "msda_fused_fwd_us": dom["us"],
                              "frames_per_sec_kernels_only": 1e6 / hot_us,

@@ -20,6 +20,7 @@
 #ifndef MVDETR_B200_H_
 #define MVDETR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -202,6 +203,25 @@ MVD_API int mvd_add_layernorm_f32(const float* x, const float* res, const float*
  *   replaces the bias/activation of `self.linear1` + F.relu  ref: mvd/models/deformable_transformer.py:82
  *   and of `value_proj`                                       ref: mvd/models/ops/modules/ms_deform_attn.py:96 */
 MVD_API int mvd_bias_act_f32(float* x, const float* bias, int64_t rows, int C, int relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Linear layer out[rows, N] = act(x[rows, K] @ W[N, K]^T + bias[N]) through the CUDA toolkit's cuBLASLt (>= 12.9, loaded
+ * by absolute path at first use: /usr/local/cuda/lib64/libcublasLt.so.12 or $MVD_CUBLASLT). Library GEMM, not a kernel
+ * of ours; what it buys on B200 is `precision` = 1: CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32 operands split into three
+ * bf16 terms, nine tensor-core products, fp32 accumulation -- fp32-level accuracy at tensor-core speed. `precision` = 0
+ * is native fp32 (CUBLAS_COMPUTE_32F) from the same library.
+ *   replaces the six nn.Linear calls per encoder layer  ref: mvd/models/ops/modules/ms_deform_attn.py:96,100-101,116,
+ *                                                        mvd/models/deformable_transformer.py:82
+ *   bias nullable; relu != 0 applies ReLU in the GEMM epilogue; all pointers 16-byte aligned; `workspace` (device,
+ *   nullable) is scratch the caller owns for the duration of the call on `stream`.
+ * Exception to the "no global state" rule: a process-wide cuBLASLt handle and a plan cache (mutex protected).
+ * Returns MVD_ERR_NO_DEVICE when no suitable cuBLASLt can be loaded, MVD_ERR_UNSUPPORTED when the library has no
+ * algorithm for the request (callers then use their own GEMM path).
+ * mvd_linear_available(): the loaded cuBLASLt version (e.g. 120901), 0 if none.
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_linear_available(void);
+MVD_API int mvd_linear_f32(const float* x, const float* W, const float* bias, int64_t rows, int K, int N, int relu,
+                   int precision, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (used for end-to-end timing and by non-PyTorch callers):

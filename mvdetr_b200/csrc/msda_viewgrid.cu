@@ -144,8 +144,10 @@ __device__ __forceinline__ void read_record(const unsigned char* base, int idx, 
   }
 }
 
+// Blocks per SM: the D=16/P=4 stage (51 KB) fits twice; larger head dims or point counts are limited to one block by
+// shared memory anyway, so they get the whole register file (no spills for the 32 accumulators of D=32).
 template <int D, int P, bool FUSED>
-__global__ void __launch_bounds__(kMaxThreads, 2)
+__global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
     msda_vg_kernel(const __grid_constant__ CUtensorMap tm_val, const __grid_constant__ CUtensorMap tm_a,
                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_ref,
                    const VgParams prm) {
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
       // ---- sample arithmetic for PC samples (ref: ms_deform_im2col_cuda.cuh:285-288, :33-84) ----
       float w1[PC], w2[PC], w3[PC], w4[PC];
       int off[PC];
-      unsigned far = 0u;  // valid samples whose footprint is not inside the window
+      unsigned far = 0u;  // valid samples whose footprint is not inside the window (handled after the window pass)
 #pragma unroll
       for (int i = 0; i < PC; ++i) {
         const float a = aw[pc + i];
@@ -301,61 +303,60 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
         const float hf = floorf(h_im), wf = floorf(w_im);
         const int h0 = v ? (int)hf : 0, w0 = v ? (int)wf : 0;
         const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-        // a sample outside the level contributes exactly 0: zero weights on the zero pad (never NaN * 0)
-        w1[i] = v ? hh * hw * a : 0.f;
-        w2[i] = v ? hh * lw * a : 0.f;
-        w3[i] = v ? lh * hw * a : 0.f;
-        w4[i] = v ? lh * lw * a : 0.f;
+        // a sample outside the level (or outside the window) contributes exactly 0 to the window pass: zero weights on
+        // the zero pad (never NaN * 0)
         const int dx = w0 - wx0, dy = h0 - wy0;
-        const bool in = (unsigned)dx < (unsigned)(BW - 1) && (unsigned)dy < (unsigned)(BH - 1);
-        off[i] = v ? (in ? (dy * BW + dx) * PX_BYTES : 0) : zoff;
+        const bool in = v && (unsigned)dx < (unsigned)(BW - 1) && (unsigned)dy < (unsigned)(BH - 1);
+        w1[i] = in ? hh * hw * a : 0.f;
+        w2[i] = in ? hh * lw * a : 0.f;
+        w3[i] = in ? lh * hw * a : 0.f;
+        w4[i] = in ? lh * lw * a : 0.f;
+        off[i] = in ? (dy * BW + dx) * PX_BYTES : zoff;
         far |= (unsigned)(v && !in) << i;
       }
-      if (__all_sync(FULL, far == 0u)) {
-        // ---- fast path: every valid sample of every lane has its 2x2 footprint in the window; no branches ----
+      // ---- window path, branch-free: far samples were given zero weights on the zero pad ----
 #pragma unroll
-        for (int i = 0; i < PC; ++i) {
+      for (int i = 0; i < PC; ++i) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+          const unsigned char* pk = win + off[i] + qoff[k];
+          const float4 v1 = *reinterpret_cast<const float4*>(pk);
+          const float4 v2 = *reinterpret_cast<const float4*>(pk + PX_BYTES);
+          const float4 v3 = *reinterpret_cast<const float4*>(pk + rowb);
+          const float4 v4 = *reinterpret_cast<const float4*>(pk + rowb + PX_BYTES);
+          fma4(acc[k], w1[i], v1, w2[i], v2, w3[i], v3, w4[i], v4);
+        }
+      }
+      // ---- far samples (2x2 footprint not inside the window): masked global loads, generic-kernel semantics. Each
+      //      lane walks its own far samples, so the warp iterates max-over-lanes(count) times, usually 0 or 1 ----
+      while (__any_sync(FULL, far != 0u)) {
+        if (far) {
+          const int i = __ffs(far) - 1;
+          far &= far - 1u;
+          // select sample i of this chunk without dynamic register indexing
+          float sx = xy[2 * pc], sy = xy[2 * pc + 1], sa = aw[pc];
+#pragma unroll
+          for (int j = 1; j < PC; ++j) {
+            sx = (i == j) ? xy[2 * (pc + j)] : sx;
+            sy = (i == j) ? xy[2 * (pc + j) + 1] : sy;
+            sa = (i == j) ? aw[pc + j] : sa;
+          }
+          const float h_im = __fsub_rn(__fmul_rn(sy, fH), 0.5f), w_im = __fsub_rn(__fmul_rn(sx, fW), 0.5f);
+          const float hf = floorf(h_im), wf = floorf(w_im);
+          const int h0 = (int)hf, w0 = (int)wf;
+          const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+          const float g1 = hh * hw * sa, g2 = hh * lw * sa, g3 = lh * hw * sa, g4 = lh * lw * sa;
+          const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
+          const float* p00 = vb + ((int64_t)l * HW + (int64_t)h0 * W + w0) * stride_px;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int k = 0; k < NQ; ++k) {
-            const unsigned char* pk = win + off[i] + qoff[k];
-            const float4 v1 = *reinterpret_cast<const float4*>(pk);
-            const float4 v2 = *reinterpret_cast<const float4*>(pk + PX_BYTES);
-            const float4 v3 = *reinterpret_cast<const float4*>(pk + rowb);
-            const float4 v4 = *reinterpret_cast<const float4*>(pk + rowb + PX_BYTES);
-            fma4(acc[k], w1[i], v1, w2[i], v2, w3[i], v3, w4[i], v4);
-          }
-        }
-      } else if (active) {
-        // ---- mixed path: per sample, window or masked global loads (generic-kernel semantics) ----
-#pragma unroll
-        for (int i = 0; i < PC; ++i) {
-          if (!((far >> i) & 1u)) {
-#pragma unroll
-            for (int k = 0; k < NQ; ++k) {
-              const unsigned char* pk = win + off[i] + qoff[k];
-              const float4 v1 = *reinterpret_cast<const float4*>(pk);
-              const float4 v2 = *reinterpret_cast<const float4*>(pk + PX_BYTES);
-              const float4 v3 = *reinterpret_cast<const float4*>(pk + rowb);
-              const float4 v4 = *reinterpret_cast<const float4*>(pk + rowb + PX_BYTES);
-              fma4(acc[k], w1[i], v1, w2[i], v2, w3[i], v3, w4[i], v4);
-            }
-          } else {
-            // rare path: recompute the top-left pixel instead of keeping it in registers across the fast path
-            const int h0 = (int)floorf(__fsub_rn(__fmul_rn(xy[2 * (pc + i) + 1], fH), 0.5f));
-            const int w0 = (int)floorf(__fsub_rn(__fmul_rn(xy[2 * (pc + i)], fW), 0.5f));
-            const bool top = h0 >= 0, bot = h0 + 1 <= H - 1, lef = w0 >= 0, rig = w0 + 1 <= W - 1;
-            const float* p00 = vb + ((int64_t)l * HW + (int64_t)h0 * W + w0) * stride_px;
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < NQ; ++k) {
-              const float* pk = p00 + (qoff[k] >> 2);
-              const float4 v1 = (top && lef) ? __ldg(reinterpret_cast<const float4*>(pk)) : z;
-              const float4 v2 = (top && rig) ? __ldg(reinterpret_cast<const float4*>(pk + stride_px)) : z;
-              const float4 v3 = (bot && lef) ? __ldg(reinterpret_cast<const float4*>(pk + (int64_t)W * stride_px)) : z;
-              const float4 v4 =
-                  (bot && rig) ? __ldg(reinterpret_cast<const float4*>(pk + (int64_t)(W + 1) * stride_px)) : z;
-              fma4(acc[k], w1[i], v1, w2[i], v2, w3[i], v3, w4[i], v4);
-            }
+            const float* pk = p00 + (qoff[k] >> 2);
+            const float4 v1 = (top && lef) ? __ldg(reinterpret_cast<const float4*>(pk)) : z;
+            const float4 v2 = (top && rig) ? __ldg(reinterpret_cast<const float4*>(pk + stride_px)) : z;
+            const float4 v3 = (bot && lef) ? __ldg(reinterpret_cast<const float4*>(pk + (int64_t)W * stride_px)) : z;
+            const float4 v4 = (bot && rig) ? __ldg(reinterpret_cast<const float4*>(pk + (int64_t)(W + 1) * stride_px)) : z;
+            fma4(acc[k], g1, v1, g2, v2, g3, v3, g4, v4);
           }
         }
       }

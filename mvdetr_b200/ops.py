@@ -282,6 +282,48 @@ def _as_nhwc(x):
     return transpose_last2(x.view(N, C, H * W)).view(N, H, W, C), True
 
 
+_GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x9")  # "bf16x9" | "fp32" (cuBLASLt 12.9 native) | "torch"
+_gemm_ws = {}
+
+
+def linear_available():
+    """cuBLASLt version behind ops.linear (>= 120900), or 0 when the toolkit library cannot be loaded."""
+    return int(_C.lib.mvd_linear_available())
+
+
+def linear(x, weight, bias=None, relu=False, mode=None):
+    """act(x @ weight.T + bias) for x [rows, K], weight [N, K] (nn.Linear layout), fp32 CUDA, through mvd_linear_f32.
+    mode "bf16x9": fp32 emulated on the tensor cores (cuBLASLt 12.9 CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32-level
+    accuracy); "fp32": the same library's native fp32; "torch": torch.mm + our bias kernel. Falls back to "torch" when
+    the library or an algorithm is unavailable (returns the same values up to fp32 rounding)."""
+    mode = mode or _GEMM_MODE
+    rows, K = x.shape
+    N = weight.shape[0]
+    x = x.contiguous()
+    if mode != "torch":
+        for name, t in (("x", x), ("weight", weight), ("bias", bias)):
+            if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise RuntimeError(f"linear: {name} must be a contiguous fp32 CUDA tensor")
+        ws = _gemm_ws.get(x.device)
+        if ws is None:
+            ws = _gemm_ws[x.device] = torch.empty(64 << 20, dtype=torch.uint8, device=x.device)
+        out = torch.empty((rows, N), dtype=x.dtype, device=x.device)
+        with _on_device(x):
+            rc = _C.lib.mvd_linear_f32(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       rows, K, N, 1 if relu else 0, 1 if mode == "bf16x9" else 0, out.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _stream(x))
+        if rc == 0:
+            return out
+        if rc not in (-3, -5):  # UNSUPPORTED / NO_DEVICE -> torch path
+            _C.check(rc, "mvd_linear_f32")
+    out = torch.mm(x, weight.t())
+    if bias is not None and N % 4 == 0:
+        return bias_act_(out, bias, relu=relu)
+    if bias is not None:
+        out = out + bias
+    return torch.relu_(out) if relu else out
+
+
 def bias_act_(x, bias, relu=False):
     """In place: x = act(x + bias) over the last dim (mvd_bias_act_f32); x is the output of a bias-free GEMM."""
     C = x.shape[-1]

@@ -125,16 +125,16 @@ class ShardedFusion:
             if nq:
                 query = src + pos
                 # bias-free GEMMs; the biases are applied inside our kernels (see world_feat.MSDeformAttn.forward)
-                offsets = torch.mm(query, attn.sampling_offsets.weight.t()).view(1, nq, M, L, P, 2)
-                logits = torch.mm(query, attn.attention_weights.weight.t()).view(1, nq, M, L * P)
+                offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
+                logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
                 out = ops.msda_fused_forward(value.view(1, S, M, C // M), geo.shapes, geo.start, offsets, logits,
                                              table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm,
                                              off_bias=attn.sampling_offsets.bias, logit_bias=attn.attention_weights.bias)
-                src2 = torch.mm(out.view(nq, C), attn.output_proj.weight.t())
+                src2 = ops.linear(out.view(nq, C), attn.output_proj.weight)
                 src = ops.add_layer_norm(src, src2, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps,
                                          res_bias=attn.output_proj.bias)
-                hidden = ops.bias_act_(torch.mm(src, layer.linear1.weight.t()), layer.linear1.bias, relu=True)
-                src2 = torch.mm(hidden, layer.linear2.weight.t())
+                hidden = ops.linear(src, layer.linear1.weight, layer.linear1.bias, relu=True)
+                src2 = ops.linear(hidden, layer.linear2.weight)
                 src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
                                          res_bias=layer.linear2.bias)
         memory = gather_rows(src, part, hw, rank, out=gbuf, group=self.group)

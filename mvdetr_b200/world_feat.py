@@ -110,9 +110,8 @@ class MSDeformAttn(nn.Module):
 
         fused = (ref_table is not None and not torch.is_grad_enabled() and input_flatten.dtype == torch.float32 and
                  input_flatten.is_cuda)
-        if fused and self.d_model % 4 == 0:
-            value = ops.bias_act_(torch.mm(input_flatten.reshape(N * Len_in, -1), self.value_proj.weight.t()),
-                                  self.value_proj.bias)
+        if fused:
+            value = ops.linear(input_flatten.reshape(N * Len_in, -1), self.value_proj.weight, self.value_proj.bias)
         else:
             value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
@@ -120,18 +119,18 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, Len_in, M, self.d_model // M)
         assert fused or not defer_output_bias, "defer_output_bias is only valid on the fused inference path"
         if fused:
-            # both Linear layers as bias-free GEMMs (cuBLASLt runs an fp32 bias as a separate pass over the 135 MB /
-            # 68 MB outputs); the biases are added inside the kernel before the same arithmetic as the reference
+            # both Linear layers as bias-free GEMMs (ops.linear: tensor-core fp32 emulation when the toolkit's cuBLASLt
+            # is available); the biases are added inside the MSDA kernel before the same arithmetic as the reference
             q2 = query.reshape(N * Len_q, -1)
-            sampling_offsets = torch.mm(q2, self.sampling_offsets.weight.t()).view(N, Len_q, M, L, P, 2)
-            attention_weights = torch.mm(q2, self.attention_weights.weight.t()).view(N, Len_q, M, L * P)
+            sampling_offsets = ops.linear(q2, self.sampling_offsets.weight).view(N, Len_q, M, L, P, 2)
+            attention_weights = ops.linear(q2, self.attention_weights.weight).view(N, Len_q, M, L * P)
             grid_hw = geometry.hw[0] if geometry is not None and geometry.uniform else None
             output = ops.msda_fused_forward(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                             sampling_offsets, attention_weights, ref_table,
                                             grid_hw=grid_hw, ref_table_lm=ref_table_lm,
                                             off_bias=self.sampling_offsets.bias, logit_bias=self.attention_weights.bias)
             if defer_output_bias:
-                return torch.mm(output.view(N * Len_q, -1), self.output_proj.weight.t()).view(N, Len_q, -1)
+                return ops.linear(output.view(N * Len_q, -1), self.output_proj.weight).view(N, Len_q, -1)
             return self.output_proj(output)
 
         sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
@@ -180,9 +179,8 @@ class DeformableTransformerEncoderLayer(nn.Module):
             # linear2 bias-free with its bias folded into the second LayerNorm kernel; same arithmetic
             src = ops.add_layer_norm(src.contiguous(), src2.contiguous(), self.norm1.weight, self.norm1.bias,
                                      self.norm1.eps, res_bias=self.self_attn.output_proj.bias if defer else None)
-            hidden = ops.bias_act_(torch.mm(src.view(-1, src.shape[-1]), self.linear1.weight.t()), self.linear1.bias,
-                                   relu=True)
-            src2 = torch.mm(hidden, self.linear2.weight.t()).view(src.shape)
+            hidden = ops.linear(src.view(-1, src.shape[-1]), self.linear1.weight, self.linear1.bias, relu=True)
+            src2 = ops.linear(hidden, self.linear2.weight).view(src.shape)
             return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps,
                                       res_bias=self.linear2.bias)
         src = self.norm1(src + self.dropout1(src2))
