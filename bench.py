@@ -279,15 +279,6 @@ def kernel_breakdown(fusion, ds, device, iters=20):
         vg = ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table, grid_hw=(Hd, Wd),
                                     ref_table_lm=wf.encoder.ref_table_lm)
         res["viewgrid_vs_generic_max_abs_diff"] = (vg - out).abs().max().item()
-        os.environ["MVD_VIEWGRID_IMPL"] = "1"  # r01a kernel (per-lane global loads of offsets/logits), A/B only
-        try:
-            t, tmin = time_kernel_events(lambda: ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits,
-                                                                        table, grid_hw=(Hd, Wd),
-                                                                        ref_table_lm=wf.encoder.ref_table_lm),
-                                         iters, flush)
-            res["msda_fused_fwd_v1"] = {"us": t, "us_min": tmin, "bytes": fb, "GBps": fb / t / 1e3}
-        finally:
-            del os.environ["MVD_VIEWGRID_IMPL"]
         t, tmin = time_kernel_events(lambda: ops.ms_deform_attn_forward(value, geo.shapes, geo.start, loc, attn, 64),
                                      iters, flush)
         ub = msda_algorithmic_bytes(1, S, HEADS, D, N, Lq, POINTS)

@@ -194,15 +194,38 @@ MVD_API int mvd_transpose_f32(const float* in, int batch, int rows, int cols, fl
  *   replaces `src = self.norm1(src + self.dropout1(src2))` / `self.norm2(src + self.dropout3(src2))`
  *       ref: mvd/models/deformable_transformer.py:79-80,84-85
  *   x, res, out [rows, C] (out may alias x or res); gamma, beta [C]; C % 4 == 0, C <= 1024, 16-byte aligned.
+ *   perm_inner > 0 (must divide rows; out must not alias): input row o*perm_inner + i is written to output row
+ *   i*(rows/perm_inner) + o, i.e. view-major tokens [N][cells] leave cell-major [cells][N], which turns the merge
+ *   convolution over all views (ref: mvd/models/trans_world_feat.py:107-108) into one GEMM over contiguous rows.
  * ------------------------------------------------------------------------------------------ */
 MVD_API int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma, const float* beta,
-                                  int64_t rows, int C, float eps, float* out, void* stream);
+                                  int64_t rows, int C, float eps, int64_t perm_inner, float* out, void* stream);
 
 /* In-place x[r, c] = act(x[r, c] + bias[c]) over [rows, C] (C % 4 == 0, 16-byte aligned), act = ReLU when `relu` != 0:
  * the bias (+ReLU) of a Linear layer whose GEMM ran bias-free.
  *   replaces the bias/activation of `self.linear1` + F.relu  ref: mvd/models/deformable_transformer.py:82
  *   and of `value_proj`                                       ref: mvd/models/ops/modules/ms_deform_attn.py:96 */
 MVD_API int mvd_bias_act_f32(float* x, const float* bias, int64_t rows, int C, int relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The two 3x3 convolutions around the encoder as GEMMs: their input is produced directly in im2col order
+ *   A[token][ky][kx][c]   (token = (view, oy, ox) row-major; tap (ky,kx) reads input pixel (oy*s+ky-1, ox*s+kx-1), zeros outside)
+ * so that conv + bias + ReLU is one mvd_linear_f32 call with the weight reshaped to [C_out, 3*3*C_in] (ky, kx, c_in order)
+ * and the GEMM's output rows are the token-major [tokens, C_out] layout the transformer consumes.
+ *   mvd_warp_im2col_f32     perspective warp (arithmetic of mvd_warp_fwd_f32) of a channels-last source [BN,Hi,Wi,C]
+ *                           onto the Ho x Wo grid, written as the im2col matrix of a 3x3 / stride s / pad 1 convolution:
+ *                           A [BN*Ho2*Wo2, 9*C], Ho2 = (Ho-1)/s + 1.   s in {1,2}, C % 4 == 0.
+ *       replaces kornia.warp_perspective + the input side of `self.downsample`
+ *                           ref: mvd/models/mvdetr.py:194-195, mvd/models/trans_world_feat.py:74,89,92
+ *   mvd_upsample_im2col_f32 bilinear upsample (ATen upsample_bilinear2d, align_corners=False) of a channels-last map
+ *                           [BN,Hi,Wi,C] to Ho x Wo, written as the im2col matrix of a 3x3 / stride 1 / pad 1
+ *                           convolution: A [BN*Ho*Wo, 9*C].
+ *       replaces nn.Upsample + the input side of the 3x3 conv   ref: mvd/models/trans_world_feat.py:83-84,109
+ * A is fully overwritten (padding slots included).
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_warp_im2col_f32(const float* src, const float* Mat, int BN, int C, int Hi, int Wi, int Ho, int Wo,
+                        int stride, float* A, void* stream);
+MVD_API int mvd_upsample_im2col_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, float* A, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Linear layer out[rows, N] = act(x[rows, K] @ W[N, K]^T + bias[N]) through the CUDA toolkit's cuBLASLt (>= 12.9, loaded

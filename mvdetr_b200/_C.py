@@ -29,7 +29,9 @@ SIGNATURES = {
     "mvd_msda_fwd_viewgrid_f32": [_p] * 3 + [_i] * 8 + [_p, _p],
     "mvd_msda_fused_fwd_f32": [_p] * 8 + [_i] * 8 + [_p] * 4,
     "mvd_msda_fused_fwd_viewgrid_f32": [_p] * 6 + [_i] * 9 + [_p] * 4,
-    "mvd_add_layernorm_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, _p, _p],
+    "mvd_add_layernorm_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p],
+    "mvd_warp_im2col_f32": [_p, _p] + [_i] * 7 + [_p, _p],
+    "mvd_upsample_im2col_f32": [_p] + [_i] * 6 + [_p, _p],
     "mvd_linear_available": [],
     "mvd_linear_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p],
     "mvd_bias_act_f32": [_p, _p, ctypes.c_int64, _i, _i, _p],

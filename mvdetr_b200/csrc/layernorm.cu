@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
                                                             const float* __restrict__ res_bias,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int64_t rows, int C,
-                                                            float eps, float* __restrict__ out) {
+                                                            float eps, int64_t perm_inner, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = 1.f / sqrtf(sq / (float)C + eps);
-  float4* orow = reinterpret_cast<float4*>(out + row * C);
+  // perm_inner > 0: rows are [outer][inner]; write them as [inner][outer] (view-major tokens -> cell-major, so the
+  // merge convolution over all views is one GEMM over contiguous rows; ref: trans_world_feat.py:107-108)
+  const int64_t orow_idx = perm_inner > 0 ? (row % perm_inner) * (rows / perm_inner) + row / perm_inner : row;
+  float4* orow = reinterpret_cast<float4*>(out + orow_idx * C);
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int i = lane + 32 * k;
@@ -110,8 +113,8 @@ extern "C" int mvd_bias_act_f32(float* x, const float* bias, int64_t rows, int C
 }
 
 extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma,
-                                     const float* beta,
-                                     int64_t rows, int C, float eps, float* out, void* stream) {
+                                     const float* beta, int64_t rows, int C, float eps, int64_t perm_inner,
+                                     float* out, void* stream) {
   if (!x || !gamma || !beta || !out) return MVD_ERR_NULL_POINTER;
   if (rows <= 0 || C <= 0) return MVD_ERR_BAD_SHAPE;
   if ((C & 3) || C > 1024) return MVD_ERR_UNSUPPORTED;
@@ -120,18 +123,19 @@ extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const flo
                        (res ? reinterpret_cast<uintptr_t>(res) : 0) |
                        (res_bias ? reinterpret_cast<uintptr_t>(res_bias) : 0);
   if (res_bias && !res) return MVD_ERR_NULL_POINTER;
+  if (perm_inner < 0 || (perm_inner > 0 && (rows % perm_inner != 0 || out == x || out == res))) return MVD_ERR_BAD_SHAPE;
   if (al & 15u) return MVD_ERR_MISALIGNED;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t blocks = ceil_div64(rows, 8);
   if (blocks > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
   if (C <= 128)
-    add_layernorm_kernel<1><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<1><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
   else if (C <= 256)
-    add_layernorm_kernel<2><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<2><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
   else if (C <= 512)
-    add_layernorm_kernel<4><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<4><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
   else
-    add_layernorm_kernel<8><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, out);
+    add_layernorm_kernel<8><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
 }

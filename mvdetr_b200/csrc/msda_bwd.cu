@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(256) msda_bwd_vec4_kernel(
       const float fH = (float)lv.H, fW = (float)lv.W;
       const float2 xy = ld_stream2(reinterpret_cast<const float*>(lp + s));
       a = ld_stream(ap + s);
-      const float h_im = __fsub_rn(__fmul_rn(xy.y, fH), 0.5f);
-      const float w_im = __fsub_rn(__fmul_rn(xy.x, fW), 0.5f);
+      const float h_im = fmaf(xy.y, fH, -0.5f);
+      const float w_im = fmaf(xy.x, fW, -0.5f);
       if (h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW) {
         const float hf = floorf(h_im), wf = floorf(w_im);
         const int h0 = (int)hf, w0 = (int)wf;

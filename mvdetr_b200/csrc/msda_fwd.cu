@@ -161,9 +161,10 @@ __global__ void __launch_bounds__(256) msda_fwd_vec4_kernel(
         xy = ld_stream2(reinterpret_cast<const float*>(lp + s));
         a = ld_stream(ap + s);
       }
-      // product rounded before the subtraction, as the reference's float*int - 0.5 (double) does (cuh:285-286)
-      const float h_im = __fsub_rn(__fmul_rn(xy.y, fH), 0.5f);
-      const float w_im = __fsub_rn(__fmul_rn(xy.x, fW), 0.5f);
+      // one fused multiply-add, as nvcc compiles the reference's `loc * spatial - 0.5` (FFMA R, R, R, -0.5 in its
+      // sm_100a SASS, cuh:285-286): same cell selection as the reference build even for samples on a pixel boundary
+      const float h_im = fmaf(xy.y, fH, -0.5f);
+      const float w_im = fmaf(xy.x, fW, -0.5f);
       if (h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW) {
         const float hf = floorf(h_im), wf = floorf(w_im);
         const int h0 = (int)hf, w0 = (int)wf;

@@ -22,15 +22,10 @@
 // zeroed pad region with zero weights (exactly 0, no branch); samples whose 2x2 footprint leaves the window take a
 // masked global-memory path, so staging changes speed, never results.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace mvd {
-
-// legacy kernel (msda_viewgrid_v1.cu), reachable with MVD_VIEWGRID_IMPL=1 for A/B timing
-int viewgrid_v1(bool fused, const float* value, const float* loc, const float* attn, const float* ref, int B, int H,
-                int W, int M, int D, int L, int R, int P, int Lr, float* out, cudaStream_t st);
 
 namespace {
 
@@ -295,9 +290,9 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
 #pragma unroll
       for (int i = 0; i < PC; ++i) {
         const float a = aw[pc + i];
-        // product rounded before the subtraction, as the reference's float*int - 0.5 does
-        const float h_im = __fsub_rn(__fmul_rn(xy[2 * (pc + i) + 1], fH), 0.5f);
-        const float w_im = __fsub_rn(__fmul_rn(xy[2 * (pc + i)], fW), 0.5f);
+        // one FFMA, exactly as nvcc compiles the reference's `loc * spatial - 0.5` (cuh:285-286)
+        const float h_im = fmaf(xy[2 * (pc + i) + 1], fH, -0.5f);
+        const float w_im = fmaf(xy[2 * (pc + i)], fW, -0.5f);
         // false for NaN and for threads without a query (tile overhang): those behave like outside samples
         const bool v = active && h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
         const float hf = floorf(h_im), wf = floorf(w_im);
@@ -341,7 +336,7 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
             sy = (i == j) ? xy[2 * (pc + j) + 1] : sy;
             sa = (i == j) ? aw[pc + j] : sa;
           }
-          const float h_im = __fsub_rn(__fmul_rn(sy, fH), 0.5f), w_im = __fsub_rn(__fmul_rn(sx, fW), 0.5f);
+          const float h_im = fmaf(sy, fH, -0.5f), w_im = fmaf(sx, fW, -0.5f);
           const float hf = floorf(h_im), wf = floorf(w_im);
           const int h0 = (int)hf, w0 = (int)wf;
           const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
@@ -445,11 +440,6 @@ int launch_vg(const CUtensorMap* maps, const VgParams& prm, const VgPlan& pl, in
   return MVD_OK;
 }
 
-bool use_v1() {
-  const char* e = getenv("MVD_VIEWGRID_IMPL");
-  return e && e[0] == '1';
-}
-
 template <bool FUSED>
 int viewgrid_dispatch(const float* value, const float* loc, const float* attn, const float* ref,
                       const float* off_bias, const float* logit_bias, int B, int H, int W, int M, int D, int L, int R,
@@ -459,8 +449,6 @@ int viewgrid_dispatch(const float* value, const float* loc, const float* attn, c
     return MVD_ERR_BAD_SHAPE;
   if (M > 65535 || B > 65535) return MVD_ERR_BAD_SHAPE;
   if (!((D == 8 || D == 16 || D == 32) && (P == 4 || P == 8))) return MVD_ERR_UNSUPPORTED;
-  if (use_v1() && !off_bias && !logit_bias)
-    return viewgrid_v1(FUSED, value, loc, attn, ref, B, H, W, M, D, L, R, P, Lr, out, st);
   if (FUSED && Lr != H * W) return MVD_ERR_UNSUPPORTED;  // table rows must be the grid cells (mvdetr.py:33-71)
   const uintptr_t al = reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(loc) |
                        reinterpret_cast<uintptr_t>(attn) | reinterpret_cast<uintptr_t>(out) |

@@ -9,6 +9,8 @@ with the model set-up of mvdetr.py:82-95,129-132 (projection table, reference ma
                     step captured in a CUDA graph, and a double-buffered host pipeline (H2D / compute / D2H on three
                     streams) for end-to-end frames from pinned host memory.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -25,6 +27,7 @@ class MultiviewFusion(nn.Module):
         self.Rworld_shape = [int(v) for v in dataset.Rworld_shape]
         self.img_reduce = dataset.img_reduce
         self.channels_last_warp = channels_last_warp
+        self.gemm_path = os.environ.get("MVDETR_B200_CONV", "gemm") != "cudnn"  # A/B switch: cuDNN convolutions
         # fp64 table kept on the host like the reference's plain attribute (mvdetr.py:93-95)
         self.proj_mats = world_grid_projection_mats(dataset, z)
         reference_points = create_reference_map(dataset, n_points).repeat([dataset.num_cam, 1, 1, 1])
@@ -42,6 +45,10 @@ class MultiviewFusion(nn.Module):
         BN, C = imgs_feat.shape[:2]
         B = BN // self.num_cam
         Hg, Wg = self.Rworld_shape
+        if B == 1 and self.gemm_path and self.world_feat.fast_path_ok(imgs_feat):
+            # inference: warp straight into the downsample conv's im2col matrix, convs as tensor-core GEMMs
+            A, (Hd, Wd) = ops.warp_im2col(imgs_feat, proj_mats, (Hg, Wg), stride=2)
+            return self.world_feat.forward_from_im2col(A, self.num_cam, Hd, Wd)
         cl = self.channels_last_warp and not torch.is_grad_enabled()
         world = ops.warp_perspective(imgs_feat, proj_mats, (Hg, Wg), align_corners=False, channels_last=cl)
         if cl:  # [BN,Hg,Wg,C] storage viewed as NCHW: the stride-2 conv then runs channels-last, no permute-copy

@@ -240,10 +240,11 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     return (out, attn, loc) if want_aux else out
 
 
-def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None):
+def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None, perm_inner=0):
     """LayerNorm(x + (res + res_bias)) over the last dim in one kernel (inference glue of the encoder layer,
     ref: multiview_detector/models/deformable_transformer.py:79-80,84-85). res may be None; res_bias [C] is the bias
-    of the Linear that produced `res` when that GEMM was run bias-free."""
+    of the Linear that produced `res` when that GEMM was run bias-free. perm_inner > 0: rows [outer][inner] are written
+    as [inner][outer] (same shape returned; see mvd_add_layernorm_f32)."""
     C = x.shape[-1]
     for name, t in (("x", x), ("res", res), ("weight", weight), ("bias", bias), ("res_bias", res_bias)):
         if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
@@ -260,6 +261,39 @@ def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None):
 
 
 _DST_NHWC, _SRC_NHWC = 1, 2  # MVD_WARP_* layout bits of include/mvdetr_b200.h
+
+
+def warp_im2col(src, M, dsize, stride=2):
+    """Perspective warp of src [BN,C,Hi,Wi] (as warp_perspective) written as the im2col matrix of a 3x3 / stride /
+    pad-1 convolution over the warped grid: returns A [BN*Ho2*Wo2, 9*C] (token-major, taps (ky,kx,c)) and (Ho2, Wo2).
+    Inference only (no autograd)."""
+    BN, C, Hi, Wi = src.shape
+    Ho, Wo = int(dsize[0]), int(dsize[1])
+    if not (src.is_cuda and src.dtype == torch.float32 and C % 4 == 0):
+        raise RuntimeError("warp_im2col: fp32 CUDA source with C % 4 == 0 required")
+    mat = M.detach().to(device=src.device, dtype=torch.float32).contiguous()
+    src_cl, _ = _as_nhwc(src)
+    Ho2, Wo2 = (Ho - 1) // stride + 1, (Wo - 1) // stride + 1
+    A = torch.empty((BN * Ho2 * Wo2, 9 * C), dtype=src.dtype, device=src.device)
+    with _on_device(src):
+        rc = _C.lib.mvd_warp_im2col_f32(src_cl.data_ptr(), mat.data_ptr(), BN, C, Hi, Wi, Ho, Wo, int(stride),
+                                        A.data_ptr(), _stream(src))
+    _C.check(rc, "mvd_warp_im2col_f32")
+    return A, (Ho2, Wo2)
+
+
+def upsample_im2col(x_cl, dsize):
+    """x_cl [BN,Hi,Wi,C] channels-last fp32 CUDA -> im2col matrix [BN*Ho*Wo, 9*C] of a 3x3 / stride-1 / pad-1 convolution
+    over its bilinear upsample (align_corners=False) to dsize."""
+    BN, Hi, Wi, C = x_cl.shape
+    Ho, Wo = int(dsize[0]), int(dsize[1])
+    if not (x_cl.is_cuda and x_cl.is_contiguous() and x_cl.dtype == torch.float32 and C % 4 == 0):
+        raise RuntimeError("upsample_im2col: contiguous fp32 CUDA [BN,Hi,Wi,C] with C % 4 == 0 required")
+    A = torch.empty((BN * Ho * Wo, 9 * C), dtype=x_cl.dtype, device=x_cl.device)
+    with _on_device(x_cl):
+        rc = _C.lib.mvd_upsample_im2col_f32(x_cl.data_ptr(), BN, C, Hi, Wi, Ho, Wo, A.data_ptr(), _stream(x_cl))
+    _C.check(rc, "mvd_upsample_im2col_f32")
+    return A
 
 
 def transpose_last2(x):

@@ -94,6 +94,9 @@ class ShardedFusion:
         if nv == 0:
             Hd, Wd = wf.pos_embedding.shape[-2:]
             return feat_local.new_zeros((0, C)), Hd, Wd
+        if self.fusion.gemm_path and wf.fast_path_ok(feat_local):
+            A, (Hd, Wd) = ops.warp_im2col(feat_local, proj_local, (Hg, Wg), stride=2)
+            return wf.tokens_from_im2col(A), Hd, Wd
         world = ops.warp_perspective(feat_local, proj_local, (Hg, Wg), align_corners=False, channels_last=True)
         x = wf.downsample(world.permute(0, 3, 1, 2))
         Hd, Wd = x.shape[-2:]
@@ -138,6 +141,9 @@ class ShardedFusion:
                 src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
                                          res_bias=layer.linear2.bias)
         memory = gather_rows(src, part, hw, rank, out=gbuf, group=self.group)
+        if self.fusion.gemm_path and wf.fast_path_ok(memory):
+            mem_cm = memory.view(N, hw, C).permute(1, 0, 2).reshape(hw, N * C)  # view-major -> cell-major rows
+            return wf.tail_from_cell_major(mem_cm, Hd, Wd)
         merged = wf.merge_linear(memory.view(1, N, Hd, Wd, C).permute(0, 1, 4, 2, 3).reshape(1, N * C, Hd, Wd))
         return wf.upsample(merged)
 

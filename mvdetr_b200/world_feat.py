@@ -167,7 +167,8 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
-                geometry=None, ref_table=None, ref_table_lm=None):
+                geometry=None, ref_table=None, ref_table_lm=None, perm_inner=0):
+        """perm_inner > 0 (inference fast path only): the layer's output rows leave cell-major, see add_layer_norm."""
         fast = (not torch.is_grad_enabled() and not self.training and src.is_cuda and src.dtype == torch.float32
                 and src.shape[-1] % 4 == 0 and src.shape[-1] <= 1024)
         defer = fast and ref_table is not None
@@ -182,7 +183,8 @@ class DeformableTransformerEncoderLayer(nn.Module):
             hidden = ops.linear(src.view(-1, src.shape[-1]), self.linear1.weight, self.linear1.bias, relu=True)
             src2 = ops.linear(hidden, self.linear2.weight).view(src.shape)
             return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps,
-                                      res_bias=self.linear2.bias)
+                                      res_bias=self.linear2.bias, perm_inner=perm_inner)
+        assert perm_inner == 0, "perm_inner is only valid on the inference fast path"
         src = self.norm1(src + self.dropout1(src2))
         src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
         return self.norm2(src + self.dropout3(src2))
@@ -225,16 +227,17 @@ class DeformableTransformerEncoder(nn.Module):
         return reference_points[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
-                geometry=None):
+                geometry=None, perm_inner_last=0):
         output = src
         if self.reference_points is None:
             hw = geometry.hw if geometry is not None else spatial_shapes.tolist()
             reference_points = self.get_reference_points(hw, valid_ratios, device=src.device)
         else:
             reference_points = self.reference_points.unsqueeze(0).expand(src.shape[0], -1, -1, -1, -1)
-        for layer in self.layers:
+        for i, layer in enumerate(self.layers):
             output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
-                           geometry=geometry, ref_table=self.ref_table, ref_table_lm=self.ref_table_lm)
+                           geometry=geometry, ref_table=self.ref_table, ref_table_lm=self.ref_table_lm,
+                           perm_inner=perm_inner_last if i == self.num_layers - 1 else 0)
         return output
 
 
@@ -274,6 +277,55 @@ class DeformTransWorldFeat(nn.Module):
         if g is None or g.shapes.device != device or g.hw != [(H, W)] * N:
             g = self._geometry = LevelGeometry([(H, W)] * N, device)
         return g
+
+    # ------------------------------------------------------------------------------------------------------------
+    # Inference fast path: both 3x3 convolutions and the 1x1 merge as Linear GEMMs over im2col / cell-major rows
+    # (csrc/im2col.cu). Same arithmetic as forward() up to fp32 summation order; used by MultiviewFusion.fuse and
+    # ShardedFusion when autograd is off.
+    # ------------------------------------------------------------------------------------------------------------
+    def gemm_weights(self):
+        """Conv weights reshaped for the GEMM path ((ky, kx, c_in) column order), cached until a weight changes."""
+        convs = (self.downsample[0], self.merge_linear[0], self.upsample[1])
+        key = tuple((c.weight.data_ptr(), c.weight._version) for c in convs)
+        if getattr(self, "_gw_key", None) != key:
+            flat = [c.weight.detach().permute(0, 2, 3, 1).reshape(c.weight.shape[0], -1).contiguous() for c in convs]
+            self._gw, self._gw_key = flat, key
+        return self._gw
+
+    def fast_path_ok(self, x):
+        return (not torch.is_grad_enabled() and not self.training and x.is_cuda and x.dtype == torch.float32 and
+                self.hidden_dim % 4 == 0 and x.shape[1] % 4 == 0 and self.stride == 2 and
+                self.encoder.ref_table is not None)
+
+    def tokens_from_im2col(self, A):
+        """A [tokens, 9*C_in] (ops.warp_im2col) -> downsample conv + ReLU as one GEMM -> [tokens, hidden]."""
+        Wd, _, _ = self.gemm_weights()
+        return ops.linear(A, Wd, self.downsample[0].bias, relu=True)
+
+    def encode_tokens(self, src, N, Hd, Wd, perm_inner_last=0):
+        """src [1, N*Hd*Wd, hidden] view-major tokens -> encoder output (cell-major rows when perm_inner_last)."""
+        B, _, C = src.shape
+        pos = (self.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
+               self.lvl_embedding.view([B, N, 1, C])).view([B, N * Hd * Wd, C])
+        geo = self._level_geometry(N, Hd, Wd, src.device)
+        return self.encoder(src, geo.shapes, geo.start, None, pos, geometry=geo, perm_inner_last=perm_inner_last)
+
+    def tail_from_cell_major(self, mem_cm, Hd, Wd):
+        """mem_cm [Hd*Wd, N*hidden] (row = ground cell, columns = (view, channel)) -> merge 1x1 conv + ReLU, bilinear
+        upsample, 3x3 conv + ReLU -> [1, hidden, Hg, Wg] (contiguous NCHW like the reference)."""
+        _, Wm, Wu = self.gemm_weights()
+        C = self.hidden_dim
+        Hg, Wg = self.Rworld_shape
+        merged = ops.linear(mem_cm, Wm, self.merge_linear[0].bias, relu=True)            # [cells, C] = NHWC map
+        A = ops.upsample_im2col(merged.view(1, Hd, Wd, C), (Hg, Wg))                      # [Hg*Wg, 9C]
+        out_cl = ops.linear(A, Wu, self.upsample[1].bias, relu=True)                     # [Hg*Wg, C]
+        return ops.transpose_last2(out_cl.view(1, Hg * Wg, C)).view(1, C, Hg, Wg)
+
+    def forward_from_im2col(self, A, N, Hd, Wd):
+        """Whole stage from the warp's im2col matrix (B = 1, as the reference): -> [1, hidden, Hg, Wg]."""
+        src = self.tokens_from_im2col(A).view(1, N * Hd * Wd, self.hidden_dim)
+        mem_cm = self.encode_tokens(src, N, Hd, Wd, perm_inner_last=Hd * Wd)
+        return self.tail_from_cell_major(mem_cm.view(Hd * Wd, N * self.hidden_dim), Hd, Wd)
 
     def forward(self, x, visualize=False):
         """x [B, N, C, H, W] (any strides; channels-last per view avoids the reference's permute-copy at

@@ -316,3 +316,13 @@ def test_bias_act_inplace(cuda, relu):
     want = torch.relu(x + b) if relu else x + b
     got = ops.bias_act_(x.clone(), b, relu=relu)
     assert torch.equal(got, want)
+
+
+def test_add_layer_norm_cell_major_output(cuda):
+    g = torch.Generator().manual_seed(11)
+    N, cells, C = 7, 60, 128
+    x, res = torch.randn(N * cells, C, generator=g).to(cuda), torch.randn(N * cells, C, generator=g).to(cuda)
+    w, b = torch.randn(C, generator=g).to(cuda), torch.randn(C, generator=g).to(cuda)
+    plain = ops.add_layer_norm(x, res, w, b, 1e-5)
+    perm = ops.add_layer_norm(x, res, w, b, 1e-5, perm_inner=cells)
+    assert torch.equal(perm.view(cells, N, C), plain.view(N, cells, C).permute(1, 0, 2))

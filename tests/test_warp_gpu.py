@@ -158,3 +158,35 @@ def test_channels_last_backward_is_the_adjoint(cuda):
 def test_transpose_kernel(cuda, batch, rows, cols):
     x = torch.randn(batch, rows, cols, generator=torch.Generator().manual_seed(rows)).to(cuda)
     assert torch.equal(ops.transpose_last2(x), x.transpose(1, 2).contiguous())
+
+
+def _im2col_reference(x_nchw, stride):
+    """[BN,C,H,W] -> [BN*Ho2*Wo2, 9*C] with (ky, kx, c) column order, via F.unfold (3x3, pad 1)."""
+    BN, C = x_nchw.shape[:2]
+    cols = torch.nn.functional.unfold(x_nchw, 3, padding=1, stride=stride)          # [BN, C*9, L], rows (c, ky, kx)
+    L = cols.shape[-1]
+    return cols.view(BN, C, 9, L).permute(0, 3, 2, 1).reshape(BN * L, 9 * C)
+
+
+@pytest.mark.parametrize("C,Hi,Wi,Ho,Wo,stride", [(128, 18, 32, 24, 72, 2), (8, 9, 16, 15, 33, 2), (132, 7, 5, 3, 11, 1),
+                                                   (16, 12, 20, 1, 1, 2), (32, 10, 10, 2, 2, 2)])
+def test_warp_im2col_matches_warp_then_unfold(cuda, C, Hi, Wi, Ho, Wo, stride):
+    rng = np.random.RandomState(C + Ho)
+    src = dev(rng.randn(3, C, Hi, Wi).astype(np.float32), cuda)
+    mats = dev(_ring_homographies(3, max(Hi, 2), max(Wi, 2), max(Ho, 2), max(Wo, 2), seed=C), cuda)
+    world = ops.warp_perspective(src, mats, (Ho, Wo), align_corners=False)
+    A, (Ho2, Wo2) = ops.warp_im2col(src, mats, (Ho, Wo), stride=stride)
+    want = _im2col_reference(world, stride)
+    assert A.shape == want.shape and Ho2 * Wo2 * 3 == want.shape[0]
+    assert torch.equal(A, want)  # same arithmetic as the warp kernel, zeros in the padding slots
+
+
+@pytest.mark.parametrize("C,Hi,Wi,Ho,Wo", [(128, 15, 45, 30, 90), (8, 7, 9, 15, 20), (36, 5, 4, 11, 6), (4, 1, 1, 3, 2)])
+def test_upsample_im2col_matches_interpolate_then_unfold(cuda, C, Hi, Wi, Ho, Wo):
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(2, C, Hi, Wi, generator=g).to(cuda)
+    up = torch.nn.functional.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=False)
+    want = _im2col_reference(up, 1)
+    A = ops.upsample_im2col(x.permute(0, 2, 3, 1).contiguous(), (Ho, Wo))
+    assert A.shape == want.shape
+    assert (A - want).abs().max().item() <= 1e-6
