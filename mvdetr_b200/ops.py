@@ -254,7 +254,8 @@ def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None, perm_inner=0):
     out = torch.empty_like(x)
     with _on_device(x):
         rc = _C.lib.mvd_add_layernorm_f32(x.data_ptr(), res.data_ptr() if res is not None else None,
-                                          res_bias.data_ptr() if res_bias is not None else None, weight.data_ptr(), bias.data_ptr(), x.numel() // C, C, float(eps),
+                                          res_bias.data_ptr() if res_bias is not None else None, weight.data_ptr(),
+                                          bias.data_ptr(), x.numel() // C, C, float(eps), int(perm_inner),
                                           out.data_ptr(), _stream(x))
     _C.check(rc, "mvd_add_layernorm_f32")
     return out

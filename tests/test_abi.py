@@ -72,3 +72,26 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "torch_port" not in text, f
+
+
+def test_every_binding_call_passes_the_declared_number_of_arguments():
+    """Static check (no GPU): each `_C.lib.mvd_*(...)` call in the package and the tests has the arity of
+    _C.SIGNATURES (a mismatch only shows up as a TypeError when the call is reached on the GPU box)."""
+    import ast
+    import glob
+    from mvdetr_b200 import _C
+    files = glob.glob(os.path.join(REPO, "mvdetr_b200", "*.py")) + glob.glob(os.path.join(REPO, "tests", "*.py")) + \
+        [os.path.join(REPO, "bench.py")]
+    seen = 0
+    for f in files:
+        for node in ast.walk(ast.parse(open(f).read())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in _C.SIGNATURES \
+                    and isinstance(node.func.value, ast.Attribute) and node.func.value.attr == "lib":
+                want = len(_C.SIGNATURES[node.func.attr])
+                starred = [a for a in node.args if isinstance(a, ast.Starred)]
+                if starred:  # ops.py passes `*aux` = (attn_out, loc_out)
+                    assert len(node.args) - len(starred) + 2 * len(starred) == want, (f, node.lineno, node.func.attr)
+                else:
+                    assert len(node.args) == want, (f, node.lineno, node.func.attr)
+                seen += 1
+    assert seen >= 15
