@@ -239,6 +239,12 @@ def kernel_breakdown(fusion, ds, device, iters=20):
         res["warp"] = warp_entry(lambda: ops.warp_perspective(feat, proj, (Hg, Wg), align_corners=False,
                                                               channels_last=True),
                                  launches="mvd_transpose_f32 + warp_fwd_cl_kernel<NHWC dst>")
+        # what the frame runner launches now: the same warp, scattered straight into the downsample conv's im2col matrix
+        # (algorithmic bytes: source read + the [tokens, 9C] matrix written)
+        ib = 4 * N * HIDDEN * ds.Rimg_shape[0] * ds.Rimg_shape[1] + 4 * N * Hd * Wd * 9 * HIDDEN + 36 * N
+        t, tmin = time_kernel_events(lambda: ops.warp_im2col(feat, proj, (Hg, Wg), stride=2), iters, flush)
+        res["warp_im2col"] = {"us": t, "us_min": tmin, "bytes": ib, "GBps": ib / t / 1e3,
+                              "launches": "mvd_transpose_f32 + warp_im2col_kernel"}
         feat_cl = feat.contiguous(memory_format=torch.channels_last)
         res["warp_cl_src"] = warp_entry(lambda: ops.warp_perspective(feat_cl, proj, (Hg, Wg), align_corners=False,
                                                                      channels_last=True),
@@ -425,7 +431,20 @@ def run_ours(args):
                     "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"],
                     "timing": "CUDA events on the launch stream, median of 20, 512 MB L2 flush before every launch"}
-        hot_us = kb["warp"]["us"] + LAYERS * dom["us"]
+        wk = kb["warp_im2col"] if fusion.gemm_path else kb["warp"]
+        hot_us = wk["us"] + LAYERS * dom["us"]
+        prof = {}
+        try:  # per-launch DRAM traffic / pipe utilisation of the dominant kernel from the committed ncu --set full capture
+            with open(os.path.join(REPO, "profiles", "ncu_dominant_kernel.json")) as f:
+                prof = json.load(f)
+        except Exception:
+            pass
+        roofline["traffic"] = prof.get("dram_bytes_per_launch")
+        roofline["traffic_source"] = prof.get("source")
+        roofline["onchip_frac"] = prof.get("l1tex_data_pipe_frac")
+        roofline["onchip_note"] = ("the kernel's binding resource is the SM L1/shared-memory data pipe (4 corners x 64 B per "
+                                   "sample = 4.33 GB of on-chip gather per launch, >= 116 us at 128 B/clk/SM); onchip_frac "
+                                   "= l1tex data-pipe utilisation from the ncu capture")
         cpu = cpu_baseline_leg() if world == 1 else None
         line = {"metric": "multiview_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -435,17 +454,20 @@ def run_ours(args):
                            "world_grid": list(ds.Rworld_shape), "layers": LAYERS, "heads": HEADS, "points": POINTS,
                            "mode": mode, "cuda_graph": True, "tf32": False,
                            "gemm": gemm_mode,
+                           "convs": "3x3 convs as im2col GEMMs (ours)" if fusion.gemm_path else "cuDNN fp32",
                            "l2": "2 alternating frame slots; per-step working set ~1.5 GB >> 126 MB L2"},
                 "roofline": roofline,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "pipeline": "pinned host -> H2D stream / graph replay / D2H stream, 2 slots"},
                 # ours per frame: transpose + warp, then per layer 1 fused MSDA + 2 add_layernorm (+ 2 bias_act when the
                 # Linear layers run through torch.mm instead of the cuBLASLt epilogues)
-                "gpu_launches": (2 + (3 if lt and _ops._GEMM_MODE != "torch" else 5) * LAYERS) * args.steps,
+                # (GEMM conv path: + upsample_im2col + the final NHWC->NCHW transpose)
+                "gpu_launches": (2 + (3 if lt and _ops._GEMM_MODE != "torch" else 5) * LAYERS +
+                                 (2 if fusion.gemm_path else 0)) * args.steps,
                 "clocks": clocks,
-                "hot_path": {"warp_us": kb["warp"]["us"], "msda_fused_fwd_us": dom["us"],
+                "hot_path": {"warp_us": wk["us"], "warp_kernel": wk.get("launches"), "msda_fused_fwd_us": dom["us"],
                              "frames_per_sec_kernels_only": 1e6 / hot_us,
-                             "warp_GBps": kb["warp"]["GBps"], "warp_frac": kb["warp"]["GBps"] / peak},
+                             "warp_GBps": wk["GBps"], "warp_frac": wk["GBps"] / peak},
                 "kernels": kb}
         if cpu is not None:
             line["cpu_baseline"] = cpu
