@@ -281,7 +281,18 @@ def kernel_breakdown(fusion, ds, device, iters=20):
                                                                     table, grid_hw=(Hd, Wd),
                                                                     ref_table_lm=wf.encoder.ref_table_lm),
                                      iters, flush)
-        res["msda_fused_fwd"] = {"us": t, "us_min": tmin, "bytes": fb, "GBps": fb / t / 1e3}
+        res["msda_fused_fwd_prebiased"] = {"us": t, "us_min": tmin, "bytes": fb, "GBps": fb / t / 1e3}
+        # exactly the frame's launch: raw (bias-free) GEMM outputs + the two Linear biases added in the kernel
+        q2 = (src + pos).view(Lq, HIDDEN)
+        raw_off = ops.linear(q2, attn_mod.sampling_offsets.weight).view(1, Lq, HEADS, N, POINTS, 2)
+        raw_log = ops.linear(q2, attn_mod.attention_weights.weight).view(1, Lq, HEADS, N * POINTS)
+        t, tmin = time_kernel_events(lambda: ops.msda_fused_forward(value, geo.shapes, geo.start, raw_off, raw_log,
+                                                                    table, grid_hw=(Hd, Wd),
+                                                                    ref_table_lm=wf.encoder.ref_table_lm,
+                                                                    off_bias=attn_mod.sampling_offsets.bias,
+                                                                    logit_bias=attn_mod.attention_weights.bias),
+                                     iters, flush)
+        res["msda_fused_fwd"] = {"us": t, "us_min": tmin, "bytes": fb + 4 * 3 * HEADS * N * POINTS, "GBps": fb / t / 1e3}
         vg = ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table, grid_hw=(Hd, Wd),
                                     ref_table_lm=wf.encoder.ref_table_lm)
         res["viewgrid_vs_generic_max_abs_diff"] = (vg - out).abs().max().item()
