@@ -56,10 +56,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
+        self.index = index
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -88,8 +89,16 @@ class ClockSampler:
             for nm, val in zip(names, f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        if not sm:  # region shorter than one sampling period: one synchronous query right after it
+            try:
+                q = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                f = [x.strip() for x in q.strip().splitlines()[0].split(",")]
+                return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]),
+                        "reasons": [nm for nm, val in zip(names, f[3:7]) if val.lower().startswith("active")],
+                        "samples": 0, "note": "timed region shorter than the sampling period; sampled right after it"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
                 "samples": len(sm)}
 
@@ -177,7 +186,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_leg(reps=3, strip=4):
@@ -483,7 +492,7 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Tear down in the order NCCL needs: the captured graphs hold the communicator's kernels, and
         # destroy_process_group() with live graphs never returns (seen on 2xB200: both ranks stuck in it).
@@ -496,10 +505,28 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else (ours, NCCL's version banner, library
+    chatter) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)   # keep the real stdout for the result line ...
+    os.dup2(2, 1)            # ... and send every other write to fd 1 (C libraries included) to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -43,6 +43,17 @@ def main():
         out, attn, loc = ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table, want_aux=True)
         ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table)
         ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits, table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm)
+        # the frame's own launch: bias-free GEMM outputs + in-kernel biases
+        q2 = (src + pos).view(Lq, C)
+        raw_off = ops.linear(q2, am.sampling_offsets.weight).view(1, Lq, H, N, P, 2)
+        raw_log = ops.linear(q2, am.attention_weights.weight).view(1, Lq, H, N * P)
+        ops.msda_fused_forward(value, geo.shapes, geo.start, raw_off, raw_log, table, grid_hw=(Hd, Wd),
+                               ref_table_lm=wf.encoder.ref_table_lm, off_bias=am.sampling_offsets.bias,
+                               logit_bias=am.attention_weights.bias)
+        A, _ = ops.warp_im2col(feat, proj, (Hg, Wg), stride=2)                      # transpose + warp_im2col_kernel
+        ops.upsample_im2col(torch.randn(1, Hd, Wd, C, device=device), (Hg, Wg))     # upsample_im2col_kernel
+        ops.add_layer_norm(src.view(S, C).contiguous(), torch.randn(S, C, device=device), wf.encoder.layers[0].norm1.weight,
+                           wf.encoder.layers[0].norm1.bias, 1e-5, res_bias=am.output_proj.bias)
         ops.ms_deform_attn_forward(value, geo.shapes, geo.start, loc, attn, 64)
         ops.ms_deform_attn_backward(value, geo.shapes, geo.start, loc, attn, torch.randn_like(out), 64)
         gw = torch.randn_like(world)

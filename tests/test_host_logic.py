@@ -65,3 +65,42 @@ def test_mirror_loads_reference_state_dict_and_projection_chain(golden):
     ref = projection.create_reference_map(ds, 4).repeat([N, 1, 1, 1])
     assert torch.equal(ref, torch.from_numpy(g["ref_points"]))
     assert model.encoder.ref_table.shape[0] * N == ref.shape[0]
+
+
+def test_conv_as_gemm_weight_layout_matches_the_im2col_definition():
+    """CPU: DeformTransWorldFeat.gemm_weights() ((ky, kx, c_in) column order) applied to the im2col matrix defined in
+    include/mvdetr_b200.h (built here with F.unfold) equals the module's own convolutions, merge conv included."""
+    import torch
+    import torch.nn.functional as F
+    from mvdetr_b200.world_feat import DeformTransWorldFeat
+
+    torch.manual_seed(0)
+    N, C, Hg, Wg = 3, 8, 10, 14
+    wf = DeformTransWorldFeat(N, [Hg, Wg], C, hidden_dim=C, nhead=2, dim_feedforward=16, n_points=4, stride=2).eval()
+    Wd, Wm, Wu = wf.gemm_weights()
+
+    def im2col(x, stride):
+        BN, Cc = x.shape[:2]
+        cols = F.unfold(x, 3, padding=1, stride=stride)
+        return cols.view(BN, Cc, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * Cc)
+
+    x = torch.randn(N, C, Hg, Wg)
+    want = wf.downsample(x)                                            # [N, C, Hd, Wd]
+    Hd, Wd_ = want.shape[-2:]
+    got = torch.relu(im2col(x, 2) @ Wd.t() + wf.downsample[0].bias)    # [N*Hd*Wd, C] token-major
+    assert torch.allclose(got.view(N, Hd, Wd_, C).permute(0, 3, 1, 2), want, atol=1e-5)
+    # merge 1x1 conv over (view, channel): cell-major rows [cells, N*C]
+    mem = torch.randn(1, N * Hd * Wd_, C)
+    want_m = wf.merge_linear(mem.view(1, N, Hd, Wd_, C).permute(0, 1, 4, 2, 3).reshape(1, N * C, Hd, Wd_))
+    mem_cm = mem.view(N, Hd * Wd_, C).permute(1, 0, 2).reshape(Hd * Wd_, N * C)
+    got_m = torch.relu(mem_cm @ Wm.t() + wf.merge_linear[0].bias)
+    assert torch.allclose(got_m.view(1, Hd, Wd_, C).permute(0, 3, 1, 2), want_m, atol=1e-5)
+    # upsample + 3x3 conv
+    want_u = wf.upsample(want_m)
+    up = F.interpolate(want_m, size=(Hg, Wg), mode="bilinear", align_corners=False)
+    got_u = torch.relu(im2col(up, 1) @ Wu.t() + wf.upsample[1].bias)
+    assert torch.allclose(got_u.view(1, Hg, Wg, C).permute(0, 3, 1, 2), want_u, atol=1e-5)
+    # cache invalidation when a weight changes in place
+    with torch.no_grad():
+        wf.downsample[0].weight.mul_(2.0)
+    assert torch.allclose(wf.gemm_weights()[0], 2.0 * Wd)
