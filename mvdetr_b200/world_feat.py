@@ -305,8 +305,12 @@ class DeformTransWorldFeat(nn.Module):
     def encode_tokens(self, src, N, Hd, Wd, perm_inner_last=0):
         """src [1, N*Hd*Wd, hidden] view-major tokens -> encoder output (cell-major rows when perm_inner_last)."""
         B, _, C = src.shape
-        pos = (self.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
-               self.lvl_embedding.view([B, N, 1, C])).view([B, N * Hd * Wd, C])
+        key = (self.lvl_embedding.data_ptr(), self.lvl_embedding._version, self.pos_embedding.data_ptr())
+        if getattr(self, "_pos_key", None) != key:  # static at inference: position + level embedding, [1, N*Hd*Wd, C]
+            self._pos = (self.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
+                         self.lvl_embedding.detach().view([B, N, 1, C])).view([B, N * Hd * Wd, C]).contiguous()
+            self._pos_key = key
+        pos = self._pos
         geo = self._level_geometry(N, Hd, Wd, src.device)
         return self.encoder(src, geo.shapes, geo.start, None, pos, geometry=geo, perm_inner_last=perm_inner_last)
 
