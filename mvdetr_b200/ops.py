@@ -109,6 +109,10 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     B, S, M, D, L, Lq, P = _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                                               im2col_step)
     out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
+    if Lq == 0:  # no queries: the reference returns its (empty) zero-initialised output (ms_deform_attn_cuda.cu:54)
+        return out
+    if S == 0:   # no keys: every sample is outside every level
+        return out.zero_()
     with _on_device(value):
         if value.dtype == torch.float32:
             geo = _viewgrid_geometry(value, spatial_shapes, S, L, Lq)
@@ -138,6 +142,8 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty_like(value)  # zeroed inside the C call
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
+    if Lq == 0 or S == 0:  # nothing sampled: all gradients are zero (ms_deform_attn_cuda.cu:121-123 zero-fills them)
+        return [grad_value.zero_(), grad_loc.zero_(), grad_attn.zero_()]
     fn = _C.lib.mvd_msda_bwd_f32 if value.dtype == torch.float32 else _C.lib.mvd_msda_bwd_f64
     with _on_device(value):
         rc = fn(grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),

@@ -326,3 +326,14 @@ def test_add_layer_norm_cell_major_output(cuda):
     plain = ops.add_layer_norm(x, res, w, b, 1e-5)
     perm = ops.add_layer_norm(x, res, w, b, 1e-5, perm_inner=cells)
     assert torch.equal(perm.view(cells, N, C), plain.view(N, cells, C).permute(1, 0, 2))
+
+
+def test_empty_query_set_behaves_like_the_reference(cuda):
+    """Lq = 0: the reference returns its zero-initialised (empty) output and zero gradients
+    (ms_deform_attn_cuda.cu:54,121-123); no kernel is launched here."""
+    value, shapes, start, loc, attn, go = make_problem(1, [(4, 5), (2, 3)], 2, 8, 3, 2, seed=1, device=cuda)
+    l0, a0, g0 = loc[:, :0].contiguous(), attn[:, :0].contiguous(), go[:, :0].contiguous()
+    out = ops.ms_deform_attn_forward(value, shapes, start, l0, a0, 64)
+    assert tuple(out.shape) == (1, 0, 16)
+    gv, gl, ga = ops.ms_deform_attn_backward(value, shapes, start, l0, a0, g0, 64)
+    assert gv.shape == value.shape and float(gv.abs().sum()) == 0.0 and gl.numel() == 0 and ga.numel() == 0
