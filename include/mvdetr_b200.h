@@ -110,6 +110,15 @@ MVD_API int mvd_msda_fwd_viewgrid_f32(const float* value, const float* loc, cons
                               int B, int H, int W, int M, int D, int L, int R, int P,
                               float* out, void* stream);
 
+/* EXPERIMENTAL (round 1: compiled and exported, not dispatched by default, not yet measured): backward for the MVDeTr
+ * encoder layout with the forward view-grid kernel's structure -- value windows and loc/attn records staged by TMA,
+ * one thread per (query, head) pair, no cross-lane reductions. Same contract and results as mvd_msda_bwd_f32 with
+ * S = L*H*W and Lq = R*H*W; grad_value is zeroed by the call. MVD_ERR_UNSUPPORTED for other (D, P) than
+ * D in {8,16,32}, P in {4,8}.   replaces ms_deform_attn_cuda_backward  ref: mvd/models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153 */
+MVD_API int mvd_msda_bwd_viewgrid_f32(const float* grad_out, const float* value, const float* loc, const float* attn,
+                              int B, int H, int W, int M, int D, int L, int R, int P,
+                              float* grad_value, float* grad_loc, float* grad_attn, void* stream);
+
 /* View-grid variant of mvd_msda_fused_fwd_f32 below (grid given as host ints; S = L*H*W, Lq = R*H*W).
  * `ref_lm` is the reference table in LEVEL-MAJOR order [L, Lr, P, 2] (query q reads row q % Lr of every level),
  * (Lr must equal H*W: one table row per ground cell). All pointers 16-byte aligned. The softmax is evaluated online (running max, one division at the

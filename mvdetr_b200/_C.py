@@ -27,6 +27,7 @@ SIGNATURES = {
     "mvd_msda_bwd_f32": [_p] * 6 + [_i] * 7 + [_p] * 4,
     "mvd_msda_bwd_f64": [_p] * 6 + [_i] * 7 + [_p] * 4,
     "mvd_msda_fwd_viewgrid_f32": [_p] * 3 + [_i] * 8 + [_p, _p],
+    "mvd_msda_bwd_viewgrid_f32": [_p] * 4 + [_i] * 8 + [_p] * 4,
     "mvd_msda_fused_fwd_f32": [_p] * 8 + [_i] * 8 + [_p] * 4,
     "mvd_msda_fused_fwd_viewgrid_f32": [_p] * 6 + [_i] * 9 + [_p] * 4,
     "mvd_add_layernorm_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p],

@@ -22,6 +22,7 @@ from torch.autograd.function import once_differentiable
 from . import _C
 
 _VIEWGRID = os.environ.get("MVDETR_B200_VIEWGRID", "1") != "0"
+_BWD_VIEWGRID = os.environ.get("MVDETR_B200_BWD_VIEWGRID", "0") == "1"  # experimental TMA-staged backward (opt-in)
 _WARP_CL = os.environ.get("MVDETR_B200_WARP_CL", "1") != "0"  # 0: always the scalar NCHW-source warp kernels (A/B switch)
 
 
@@ -144,6 +145,19 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_attn = torch.empty_like(attn_weight)
     if Lq == 0 or S == 0:  # nothing sampled: all gradients are zero (ms_deform_attn_cuda.cu:121-123 zero-fills them)
         return [grad_value.zero_(), grad_loc.zero_(), grad_attn.zero_()]
+    if _BWD_VIEWGRID and value.dtype == torch.float32:  # experimental opt-in (round 1: not the default path)
+        geo = _viewgrid_geometry(value, spatial_shapes, S, L, Lq)
+        if geo is not None:
+            H, W, R = geo
+            with _on_device(value):
+                rc = _C.lib.mvd_msda_bwd_viewgrid_f32(grad_output.data_ptr(), value.data_ptr(), sampling_loc.data_ptr(),
+                                                      attn_weight.data_ptr(), B, H, W, M, D, L, R, P,
+                                                      grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+                                                      _stream(value))
+            if rc == 0:
+                return [grad_value, grad_loc, grad_attn]
+            if rc != -3:
+                _C.check(rc, "mvd_msda_bwd_viewgrid_f32")
     fn = _C.lib.mvd_msda_bwd_f32 if value.dtype == torch.float32 else _C.lib.mvd_msda_bwd_f64
     with _on_device(value):
         rc = fn(grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),

@@ -1,6 +1,8 @@
 """GPU parity tests for multi-scale deformable attention: CUDA (through the C ABI) vs the CPU oracle, the committed
 golden vectors produced by the reference's Python core, the reference's own CUDA op (when oracle/_ref was built),
 and size-independent properties at BASELINE.json's full Wildtrack size."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -337,3 +339,21 @@ def test_empty_query_set_behaves_like_the_reference(cuda):
     assert tuple(out.shape) == (1, 0, 16)
     gv, gl, ga = ops.ms_deform_attn_backward(value, shapes, start, l0, a0, g0, 64)
     assert gv.shape == value.shape and float(gv.abs().sum()) == 0.0 and gl.numel() == 0 and ga.numel() == 0
+
+
+@pytest.mark.skipif(os.environ.get("MVDETR_B200_BWD_VIEWGRID", "0") != "1",
+                    reason="experimental view-grid backward: opt-in (MVDETR_B200_BWD_VIEWGRID=1), not yet validated")
+@pytest.mark.parametrize("L,H,W,M,D,P,R,offset_px", [(7, 30, 45, 8, 16, 4, 7, 3.0), (7, 30, 45, 8, 16, 4, 7, 40.0),
+                                                     (3, 13, 21, 2, 16, 4, 5, 8.0), (6, 9, 50, 4, 32, 8, 6, 5.0)])
+def test_experimental_viewgrid_backward_matches_generic(cuda, L, H, W, M, D, P, R, offset_px):
+    value, shapes, start, loc, attn, go = (t.to(cuda) for t in viewgrid_problem(L, H, W, M, D, P, seed=9, R=R,
+                                                                               offset_px=offset_px))
+    got = ops.ms_deform_attn_backward(value, shapes, start, loc, attn, go, 64)      # opt-in kernel (env set)
+    old = ops._BWD_VIEWGRID
+    try:
+        ops._BWD_VIEWGRID = False
+        want = ops.ms_deform_attn_backward(value, shapes, start, loc, attn, go, 64)  # generic kernel
+    finally:
+        ops._BWD_VIEWGRID = old
+    for a, b in zip(got, want):
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
