@@ -1,13 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- multiview fusion frames/s on synthetic Wildtrack-shaped input (BASELINE.json configs[1]).
+"""bench.py -- multiview fusion frames/s on synthetic input (BASELINE.json configs[1] by default).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA kernels behind the C ABI)
-  python bench.py --impl reference [...]                          the reference's CPU-capable path (oracle port)
-  torchrun --nproc-per-node N ... bench.py --gpus N ...           N>1: camera views sharded across ranks
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wildtrack|multiviewx|stress4k]
+        our arm (CUDA kernels behind the C ABI)
+  python bench.py --impl reference [...]
+        the reference's CPU-capable path (oracle port, no product import, all host threads)
+  torchrun --nproc-per-node N ... bench.py --gpus N ...
+        N>1: camera views sharded across ranks
 
-One step = one frame through the fusion stage of MVDeTr.forward: perspective warp of the 7 per-view feature maps
-[7,128,90,160] -> [7,128,120,360] followed by DeformTransWorldFeat (3 deformable-attention encoder layers), i.e.
+One step = one frame through the fusion stage of MVDeTr.forward: perspective warp of the per-view feature maps onto
+the ground grid followed by DeformTransWorldFeat (3 deformable-attention encoder layers), i.e.
 ref multiview_detector/models/mvdetr.py:194-202. The backbone is out of scope; features are synthetic.
+Workloads (BASELINE.json configs[1..3]):
+  wildtrack   7 views, features [7,128,90,160] -> ground grid 120x360, C=128, 8 heads x D=16, 4 points   (headline)
+  multiviewx  6 views, features [6,128,90,160] -> ground grid 160x250, same model; on 8 GPUs ranks 6-7 hold no view
+  stress4k    8 views of 4K, features [8,256,180,320] -> ground grid 240x720, C=256, 8 heads x D=32, 8 points
 Prints ONE JSON line (see the keys below); everything else goes to stderr.
 """
 import argparse
@@ -23,8 +30,15 @@ import torch
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-WORKLOAD = "wildtrack_7view_1080p_resnet18feat_deform_trans"
-HIDDEN, HEADS, POINTS, LAYERS = 128, 8, 4, 3
+LAYERS = 3
+WORKLOADS = {
+    "wildtrack": dict(label="wildtrack_7view_1080p_resnet18feat_deform_trans", scene="wildtrack_like", hidden=128,
+                      heads=8, points=4, cpu_strip=1),
+    "multiviewx": dict(label="multiviewx_6view_1080p_resnet18feat_deform_trans", scene="multiviewx_like", hidden=128,
+                       heads=8, points=4, cpu_strip=1),
+    "stress4k": dict(label="stress_8view_4k_c256_d32_p8_deform_trans", scene="stress4k_like", hidden=256, heads=8,
+                     points=8, cpu_strip=8),
+}
 
 
 def log(*a):
@@ -46,6 +60,7 @@ def msda_algorithmic_bytes(B, S, M, D, L, Lq, P, fused_ref_rows=0):
 
 
 def warp_algorithmic_bytes(BN, C, Hi, Wi, Ho, Wo):
+    """source read once + warped grid written once (what the reference's op boundary moves)."""
     return 4 * BN * C * (Hi * Wi + Ho * Wo) + 36 * BN
 
 
@@ -103,15 +118,111 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_fusion(device, seed=0):
-    """Random-init fusion stage with Wildtrack geometry; offsets/attention made query dependent (SURVEY 8d config 2:
-    default init has zero weight => every query samples the same fixed ring, an unrealistically cache-friendly
+def workload_config(wl, sc_num_cam, feat_shape, world_grid):
+    return {"workload": wl["label"], "views": sc_num_cam, "feat": list(feat_shape), "world_grid": list(world_grid),
+            "layers": LAYERS, "heads": wl["heads"], "points": wl["points"], "hidden": wl["hidden"]}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU-capable path restated in oracle/ (kind "port"). Imports NOTHING from the product
+# package: the problem (calibration, projection chain, reference table, weights) comes from oracle/ref_problem.py.
+# ------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    """All host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the CPU
+    arm into a single-thread run."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_problem(wl_name, seed=0):
+    from oracle import ref_problem
+    from oracle import torch_port as tp
+    wl = WORKLOADS[wl_name]
+    p = ref_problem.problem(wl_name, seed=seed, strip=wl["cpu_strip"])
+    Hg, Wg = p["sc"]["Rworld"]
+    p["pos"] = tp.sine_pos_embedding((Hg // 2, Wg // 2), wl["hidden"] // 2)  # built once, as the reference's ctor does
+    p["wl"] = wl
+    return p
+
+
+def cpu_step(p):
+    from oracle import torch_port as tp
+    sc, wl = p["sc"], p["wl"]
+    with torch.no_grad():
+        world = tp.warp_perspective(p["feat"], p["proj"], tuple(sc["Rworld"]))
+        return tp.world_feat_forward(p["sd"], world.view(1, sc["num_cam"], wl["hidden"], *sc["Rworld"]), p["ref"],
+                                     n_heads=wl["heads"], n_points=wl["points"], n_layers=LAYERS,
+                                     pos_embedding=p["pos"])
+
+
+def cpu_sample_text(p):
+    sc, wl = p["sc"], p["wl"]
+    full = "the FULL frame" if wl["cpu_strip"] == 1 else f"a 1/{wl['cpu_strip']} column strip of the ground grid"
+    return (f"{full}: all {sc['num_cam']} views [{sc['num_cam']},{wl['hidden']},{sc['Rimg'][0]},{sc['Rimg'][1]}] -> "
+            f"{sc['Rworld'][0]}x{sc['Rworld'][1]} ground cells, 3 encoder layers, merge + upsample; fp32 torch CPU")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = cpu_threads()
+    p = cpu_problem(args.workload)
+    strip = p["wl"]["cpu_strip"]
+    for _ in range(max(1, args.warmup)):
+        cpu_step(p)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(p)
+    dt = (time.perf_counter() - t0) / args.steps
+    fps = (1.0 / strip) / dt
+    sc = p["sc"]
+    full = ref_full_dims(args.workload)
+    line = {"impl": "reference", "metric": "multiview_frames_per_sec", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(p["wl"], sc["num_cam"], (sc["num_cam"], p["wl"]["hidden"], *sc["Rimg"]), full),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": cpu_sample_text(p), "host_cpus": os.cpu_count(),
+                             "frames_per_step": 1.0 / strip},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    emit(line)
+
+
+def ref_full_dims(wl_name):
+    from oracle import ref_problem
+    w = ref_problem.WORKLOADS[wl_name]
+    return [w["grid"][0] // w["world_reduce"], w["grid"][1] // w["world_reduce"]]
+
+
+def cpu_baseline_leg(wl_name, reps=3):
+    cores = cpu_threads()
+    p = cpu_problem(wl_name)
+    strip = p["wl"]["cpu_strip"]
+    cpu_step(p)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_step(p)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": (1.0 / strip) / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} reps of {cpu_sample_text(p)}", "host_cpus": os.cpu_count(),
+            "seconds_per_frame_equiv": dt * strip}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def build_fusion(device, wl, seed=0):
+    """Random-init fusion stage with the workload's geometry; offsets/attention made query dependent (SURVEY 8d config
+    2: default init has zero weight => every query samples the same fixed ring, an unrealistically cache-friendly
     pattern)."""
     from mvdetr_b200 import synthetic
     from mvdetr_b200.fusion import MultiviewFusion
     torch.manual_seed(seed)
-    ds = synthetic.wildtrack_like(seed=seed)
-    fusion = MultiviewFusion(ds, base_dim=HIDDEN, hidden_dim=HIDDEN, nhead=HEADS, n_points=POINTS)
+    ds = getattr(synthetic, wl["scene"])(seed=seed)
+    fusion = MultiviewFusion(ds, base_dim=wl["hidden"], hidden_dim=wl["hidden"], nhead=wl["heads"],
+                             n_points=wl["points"])
     with torch.no_grad():
         for layer in fusion.world_feat.encoder.layers:
             layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
@@ -119,91 +230,16 @@ def build_fusion(device, seed=0):
     return ds, fusion.to(device).eval()
 
 
-def synthetic_frames(ds, n, seed=0, pin=False):
+def synthetic_frames(ds, hidden, n, seed=0, pin=False):
     g = torch.Generator().manual_seed(seed)
     feats, Ms = [], []
     for _ in range(n):
-        f = torch.randn(ds.num_cam, HIDDEN, *ds.Rimg_shape, generator=g)
+        f = torch.randn(ds.num_cam, hidden, *ds.Rimg_shape, generator=g)
         feats.append(f.pin_memory() if pin else f)
         Ms.append(torch.eye(3).view(1, 1, 3, 3).repeat(1, ds.num_cam, 1, 1))
     return feats, Ms
 
 
-# ------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's CPU-capable path restated in oracle/torch_port.py (kind "port")
-# ------------------------------------------------------------------------------------------------------------
-def cpu_strip_problem(seed=0, strip=4):
-    """Bounded sample of the workload: all 7 views, but a 1/strip-wide strip of the ground grid (120 x 360/strip).
-    Every stage of the path is linear in the number of ground cells, so frames/s = (1/strip) / seconds."""
-    from mvdetr_b200 import synthetic
-    from mvdetr_b200.projection import create_reference_map, frame_projection_mats, world_grid_projection_mats
-    from mvdetr_b200.world_feat import DeformTransWorldFeat
-    torch.manual_seed(seed)
-    ds = synthetic.wildtrack_like(seed=seed)
-    ds.Rworld_shape = [ds.Rworld_shape[0], ds.Rworld_shape[1] // strip]
-    ref = create_reference_map(ds, POINTS).repeat([ds.num_cam, 1, 1, 1])
-    model = DeformTransWorldFeat(ds.num_cam, ds.Rworld_shape, HIDDEN, hidden_dim=HIDDEN, nhead=HEADS,
-                                 n_points=POINTS, reference_points=ref).eval()
-    with torch.no_grad():
-        for layer in model.encoder.layers:
-            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
-            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
-    proj = frame_projection_mats(world_grid_projection_mats(ds), torch.eye(3).view(1, 1, 3, 3).repeat(1, 7, 1, 1),
-                                 ds.img_reduce)
-    feats, _ = synthetic_frames(ds, 1, seed)
-    return ds, sd, ref, proj, feats[0]
-
-
-def cpu_step(ds, sd, ref, proj, feat):
-    from oracle import torch_port as tp
-    with torch.no_grad():
-        world = tp.warp_perspective(feat, proj, tuple(ds.Rworld_shape))
-        return tp.world_feat_forward(sd, world.view(1, ds.num_cam, HIDDEN, *ds.Rworld_shape), ref, n_heads=HEADS,
-                                     n_points=POINTS, n_layers=LAYERS)
-
-
-def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    strip = 4
-    prob = cpu_strip_problem(strip=strip)
-    cores = torch.get_num_threads()
-    for _ in range(max(1, args.warmup)):
-        cpu_step(*prob)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_step(*prob)
-    dt = (time.perf_counter() - t0) / args.steps
-    fps = (1.0 / strip) / dt
-    sample = f"all 7 views, 120x{360 // strip} strip (1/{strip}) of the 120x360 ground grid per step; fp32 torch CPU"
-    line = {"impl": "reference", "metric": "multiview_frames_per_sec", "value": fps, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "views": 7, "feat": [7, HIDDEN, 90, 160], "world_grid": [120, 360],
-                       "layers": LAYERS, "heads": HEADS, "points": POINTS},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
-                             "host_cpus": os.cpu_count()},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    emit(line)
-
-
-def cpu_baseline_leg(reps=3, strip=4):
-    prob = cpu_strip_problem(strip=strip)
-    cpu_step(*prob)
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        cpu_step(*prob)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": (1.0 / strip) / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{reps} reps of all 7 views on a 120x{360 // strip} strip (1/{strip}) of the ground grid",
-            "host_cpus": os.cpu_count(), "seconds_per_frame_equiv": dt * strip}
-
-
-# ------------------------------------------------------------------------------------------------------------
-# GPU arm
-# ------------------------------------------------------------------------------------------------------------
 def time_kernel_events(fn, iters, flush=None):
     """(median, min) device time of fn() in microseconds: CUDA events on the current stream, 3 untimed warm-ups,
     optional L2 flush (a write larger than L2) before every timed launch."""
@@ -223,11 +259,23 @@ def time_kernel_events(fn, iters, flush=None):
     return statistics.median(ts), min(ts)
 
 
-def kernel_breakdown(fusion, ds, device, iters=20):
-    """Per-kernel device times for the two hot-path kernels on this workload's real tensors (L2 flushed between
+def load_ref_ext():
+    ref_so = os.path.join(REPO, "oracle", "_ref", "MultiScaleDeformableAttention.so")
+    if not os.path.exists(ref_so):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttention", ref_so)
+    ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ext)
+    return ext
+
+
+def kernel_breakdown(fusion, ds, wl, device, iters=20):
+    """Per-kernel device times for the hot-path kernels on this workload's real tensors (L2 flushed between
     launches with a 512 MB memset), plus the reference's own CUDA op on the same inputs when oracle/_ref exists."""
     from mvdetr_b200 import ops
     wf = fusion.world_feat
+    HIDDEN, HEADS, POINTS = wl["hidden"], wl["heads"], wl["points"]
     N, (Hg, Wg) = ds.num_cam, ds.Rworld_shape
     Hd, Wd = Hg // 2, Wg // 2
     Lq = S = N * Hd * Wd
@@ -244,34 +292,28 @@ def kernel_breakdown(fusion, ds, device, iters=20):
             t, tmin = time_kernel_events(fn, iters, flush)
             return dict({"us": t, "us_min": tmin, "bytes": wb, "GBps": wb / t / 1e3}, **extra)
 
-        # as the frame runner calls it: NCHW features in (the backbone's layout), channels-last world grid out
+        # NCHW features in (the backbone's layout), channels-last world grid out
         res["warp"] = warp_entry(lambda: ops.warp_perspective(feat, proj, (Hg, Wg), align_corners=False,
                                                               channels_last=True),
-                                 launches="mvd_transpose_f32 + warp_fwd_cl_kernel<NHWC dst>")
-        # what the frame runner launches now: the same warp, scattered straight into the downsample conv's im2col matrix
-        # (algorithmic bytes: source read + the [tokens, 9C] matrix written)
+                                 launches=ops.warp_launch_names(feat, channels_last=True))
+        # what the frame runner launches: the same warp, written straight into the downsample conv's im2col matrix.
+        # `bytes` / GBps use SURVEY 8(d)'s ALGORITHMIC warp bytes (source + warped grid once); `written_bytes` is what
+        # the kernel really stores ([tokens, 9C] matrix = 2.25 copies of the grid)
         ib = 4 * N * HIDDEN * ds.Rimg_shape[0] * ds.Rimg_shape[1] + 4 * N * Hd * Wd * 9 * HIDDEN + 36 * N
         t, tmin = time_kernel_events(lambda: ops.warp_im2col(feat, proj, (Hg, Wg), stride=2), iters, flush)
-        res["warp_im2col"] = {"us": t, "us_min": tmin, "bytes": ib, "GBps": ib / t / 1e3,
-                              "launches": "mvd_transpose_f32 + warp_im2col_kernel"}
+        res["warp_im2col"] = {"us": t, "us_min": tmin, "bytes": wb, "GBps": wb / t / 1e3, "moved_bytes": ib,
+                              "moved_GBps": ib / t / 1e3, "launches": ops.warp_launch_names(feat, im2col=True)}
         feat_cl = feat.contiguous(memory_format=torch.channels_last)
         res["warp_cl_src"] = warp_entry(lambda: ops.warp_perspective(feat_cl, proj, (Hg, Wg), align_corners=False,
                                                                      channels_last=True),
-                                        launches="warp_fwd_cl_kernel<NHWC dst> on a channels_last source")
+                                        launches=ops.warp_launch_names(feat_cl, channels_last=True))
         res["warp_nchw_contract"] = warp_entry(lambda: ops.warp_perspective(feat, proj, (Hg, Wg),
                                                                             align_corners=False),
-                                               launches="mvd_transpose_f32 + warp_fwd_cl_kernel<NCHW dst>")
-        ops._WARP_CL = False
-        try:
-            res["warp_scalar_nchw_src"] = warp_entry(lambda: ops.warp_perspective(feat, proj, (Hg, Wg),
-                                                                                  align_corners=False,
-                                                                                  channels_last=True),
-                                                     launches="warp_fwd_nhwc_kernel (r01a kernel)")
-        finally:
-            ops._WARP_CL = True
+                                               launches=ops.warp_launch_names(feat, channels_last=False))
         # realistic MSDA inputs: run the model's own first layer projections on a real frame
         world = ops.warp_perspective(feat, proj, (Hg, Wg), align_corners=False).view(1, N, HIDDEN, Hg, Wg)
         x = wf.downsample(world.view(N, HIDDEN, Hg, Wg))
+        del world
         src = x.view(1, N, HIDDEN, Hd, Wd).permute(0, 1, 3, 4, 2).reshape(1, S, HIDDEN)
         pos = (wf.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) + wf.lvl_embedding.view(1, N, 1, HIDDEN)
                ).view(1, S, HIDDEN)
@@ -286,11 +328,6 @@ def kernel_breakdown(fusion, ds, device, iters=20):
                                                                     table), iters, flush)
         fb = msda_algorithmic_bytes(1, S, HEADS, D, N, Lq, POINTS, fused_ref_rows=table.shape[0])
         res["msda_fused_fwd_generic"] = {"us": t, "us_min": tmin, "bytes": fb, "GBps": fb / t / 1e3}
-        t, tmin = time_kernel_events(lambda: ops.msda_fused_forward(value, geo.shapes, geo.start, offsets, logits,
-                                                                    table, grid_hw=(Hd, Wd),
-                                                                    ref_table_lm=wf.encoder.ref_table_lm),
-                                     iters, flush)
-        res["msda_fused_fwd_prebiased"] = {"us": t, "us_min": tmin, "bytes": fb, "GBps": fb / t / 1e3}
         # exactly the frame's launch: raw (bias-free) GEMM outputs + the two Linear biases added in the kernel
         q2 = (src + pos).view(Lq, HIDDEN)
         raw_off = ops.linear(q2, attn_mod.sampling_offsets.weight).view(1, Lq, HEADS, N, POINTS, 2)
@@ -313,14 +350,11 @@ def kernel_breakdown(fusion, ds, device, iters=20):
         t, tmin = time_kernel_events(lambda: ops.ms_deform_attn_backward(value, geo.shapes, geo.start, loc, attn, go,
                                                                          64), max(5, iters // 2), flush)
         bb = 4 * (3 * S * HEADS * D + Lq * HEADS * D + 2 * 3 * Lq * HEADS * N * POINTS)
-        res["msda_bwd"] = {"us": t, "us_min": tmin, "bytes": bb, "GBps": bb / t / 1e3}
-        ref_so = os.path.join(REPO, "oracle", "_ref", "MultiScaleDeformableAttention.so")
-        if os.path.exists(ref_so):
-            try:
-                import importlib.util
-                spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttention", ref_so)
-                ext = importlib.util.module_from_spec(spec)
-                spec.loader.exec_module(ext)
+        res["msda_bwd"] = {"us": t, "us_min": tmin, "bytes": bb, "GBps": bb / t / 1e3,
+                           "kernel": ops.msda_bwd_kernel_name(value, geo.hw, Lq)}
+        try:  # comparator only; never fatal
+            ext = load_ref_ext()
+            if ext is not None:
                 t, tmin = time_kernel_events(lambda: ext.ms_deform_attn_forward(value, geo.shapes, geo.start, loc,
                                                                                 attn, 64), iters, flush)
                 res["ref_cuda_msda_fwd"] = {"us": t, "us_min": tmin, "GBps": ub / t / 1e3}
@@ -330,10 +364,76 @@ def kernel_breakdown(fusion, ds, device, iters=20):
                 res["ref_cuda_msda_bwd"] = {"us": t, "us_min": tmin, "GBps": bb / t / 1e3}
                 diff = (ext.ms_deform_attn_forward(value, geo.shapes, geo.start, loc, attn, 64) - out).abs().max()
                 res["ref_cuda_max_abs_diff"] = diff.item()
-            except Exception as e:  # comparator only; never fatal
-                res["ref_cuda_error"] = repr(e)[:200]
+        except Exception as e:
+            res["ref_cuda_error"] = repr(e)[:200]
     del flush
     return res
+
+
+def ref_cuda_frame(fusion, ds, wl, device, ours_out, feat, proj, iters=10):
+    """SURVEY 8(d) "Reference comparators (i)": the reference's frame on the SAME B200 -- its DeformTransWorldFeat
+    arithmetic (trans_world_feat.py:87-110, restated functionally in oracle/torch_port.py over the same weights),
+    kornia-style warp through F.grid_sample, cuDNN convolutions / cuBLAS Linear layers through torch, and the
+    reference's OWN CUDA op (oracle/_ref, its sources compiled for sm_100a) for the deformable attention.
+      as_shipped   with the per-frame host->device uploads of the position embedding (trans_world_feat.py:93) and the
+                   repeated reference-point table (deformable_transformer.py:48) and the device->host assert
+                   (ms_deform_attn.py:94); wall clock around synchronised frames
+      kernels_only those tensors already resident, no assert; CUDA events
+    COMPARATOR ONLY: nothing here is on the product path."""
+    ext = load_ref_ext()
+    if ext is None:
+        return {"unavailable": "oracle/_ref/MultiScaleDeformableAttention.so not built"}
+    from oracle import torch_port as tp
+    wf = fusion.world_feat
+    N, (Hg, Wg) = ds.num_cam, ds.Rworld_shape
+    sd = {k: v.detach() for k, v in wf.state_dict().items()}
+    ref_host = wf.encoder.reference_points.detach().cpu()        # [N*Hd*Wd, N, P, 2], as mvdetr.py:129-130 builds it
+    pos_host = wf.pos_embedding.detach().cpu()
+    ref_dev, pos_dev = ref_host.to(device), pos_host.to(device)
+
+    def msda_fn(value, shapes, start, loc, attn):
+        return ext.ms_deform_attn_forward(value.contiguous(), shapes, start, loc.contiguous(), attn.contiguous(), 64)
+
+    def frame(ref, pos, sync_assert):
+        world = tp.warp_perspective(feat, proj, (Hg, Wg))
+        return tp.world_feat_forward(sd, world.view(1, N, wl["hidden"], Hg, Wg), ref, n_heads=wl["heads"],
+                                     n_points=wl["points"], n_layers=LAYERS, pos_embedding=pos, msda_fn=msda_fn,
+                                     sync_assert=sync_assert)
+
+    res = {}
+    with torch.no_grad():
+        for _ in range(3):
+            out = frame(ref_dev, pos_dev, False)
+        res["max_abs_diff_vs_ours"] = (out - ours_out).abs().max().item()
+        t, tmin = time_kernel_events(lambda: frame(ref_dev, pos_dev, False), iters)
+        res["kernels_only"] = {"ms": t / 1e3, "ms_min": tmin / 1e3, "frames_per_sec": 1e6 / t}
+        for _ in range(2):
+            frame(ref_host, pos_host, True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            frame(ref_host, pos_host, True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / iters
+        res["as_shipped"] = {"ms": dt * 1e3, "frames_per_sec": 1.0 / dt,
+                             "h2d_bytes_per_frame": ref_host.numel() * 4 + pos_host.numel() * 4}
+    res["what"] = ("reference DeformTransWorldFeat arithmetic + F.grid_sample warp + the reference's own CUDA op "
+                   "(oracle/_ref) + cuDNN/cuBLAS fp32 through torch, same weights and inputs, same GPU; features "
+                   "already on the device in both variants")
+    return res
+
+
+def our_launches_per_frame(fusion, lt_gemm):
+    """OUR kernels per frame (library GEMMs not counted): warp (1 launch when the TMA kernel takes the NCHW source, else
+    relayout + gather), then per layer 1 fused MSDA + 2 add_layernorm (+ 2 bias_act when the Linear layers run through
+    torch.mm), the query add of the 2nd/3rd layer folded into the previous LayerNorm, plus upsample_im2col and the
+    final NHWC->NCHW transpose on the GEMM conv path."""
+    from mvdetr_b200 import ops
+    n = ops.warp_launch_count(im2col=fusion.gemm_path)
+    n += (3 if lt_gemm else 5) * LAYERS
+    n += ops.pos_add_launches(LAYERS)
+    n += 2 if fusion.gemm_path else 0
+    return n
 
 
 def run_ours(args):
@@ -344,6 +444,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference "
                          "for the CPU arm)")
+    wl = WORKLOADS[args.workload]
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     torch.backends.cuda.matmul.allow_tf32 = False  # dense glue stays full fp32, like the reference
@@ -362,7 +463,8 @@ def run_ours(args):
             faulthandler.dump_traceback_later(float(os.environ["MVD_BENCH_TRACE"]), exit=True, file=sys.stderr)
 
     from mvdetr_b200.fusion import FrameRunner
-    ds, fusion = build_fusion(device)
+    HIDDEN = wl["hidden"]
+    ds, fusion = build_fusion(device, wl)
     BN = ds.num_cam
     feat_shape = (BN, HIDDEN, *ds.Rimg_shape)
     if world > 1:
@@ -373,8 +475,8 @@ def run_ours(args):
         runner = FrameRunner(fusion, feat_shape, device, use_graph=True, depth=2)
         mode = "single"
 
-    n_frames = 4  # distinct synthetic frames cycled through (4 x 51.6 MB of features > L2)
-    feats_pinned, Ms = synthetic_frames(ds, n_frames, seed=0, pin=True)
+    n_frames = 4 if args.workload != "stress4k" else 2  # distinct synthetic frames cycled through (> L2 in total)
+    feats_pinned, Ms = synthetic_frames(ds, HIDDEN, n_frames, seed=0, pin=True)
     feats_dev = [f.to(device) for f in feats_pinned]
     projs_dev = [fusion.projection(M).to(device) for M in Ms]
     out_shape = (1, HIDDEN, *ds.Rworld_shape)
@@ -440,13 +542,15 @@ def run_ours(args):
     line = None
     from mvdetr_b200 import ops as _ops
     lt = _ops.linear_available()
-    gemm_mode = (f"{_ops._GEMM_MODE} via cuBLASLt {lt} (fp32 in/out; bf16x9 = CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32-accurate "
-                 f"tensor-core emulation)" if lt and _ops._GEMM_MODE != "torch" else "torch.mm fp32 (cuBLAS SIMT)")
+    lt_gemm = bool(lt) and _ops._GEMM_MODE != "torch"
+    gemm_mode = _ops.gemm_mode_text()
     if rank == 0:
-        kb = kernel_breakdown(fusion, ds, device)
+        kb = kernel_breakdown(fusion, ds, wl, device, iters=20 if args.workload != "stress4k" else 6)
         peak, peak_src = measured_peak_hbm()
         dom = kb["msda_fused_fwd"]
-        roofline = {"kernel": "msda_vg_kernel<16,4,FUSED> (mvd_msda_fused_fwd_viewgrid_f32), 3 launches/step",
+        D = HIDDEN // wl["heads"]
+        roofline = {"kernel": f"msda_vg_kernel<{D},{wl['points']},FUSED> (mvd_msda_fused_fwd_viewgrid_f32), "
+                              f"{LAYERS} launches/step",
                     "bound": "hbm", "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": dom["GBps"] / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"],
@@ -454,43 +558,56 @@ def run_ours(args):
         wk = kb["warp_im2col"] if fusion.gemm_path else kb["warp"]
         hot_us = wk["us"] + LAYERS * dom["us"]
         prof = {}
-        try:  # per-launch DRAM traffic / pipe utilisation of the dominant kernel from the committed ncu --set full capture
-            with open(os.path.join(REPO, "profiles", "ncu_dominant_kernel.json")) as f:
-                prof = json.load(f)
-        except Exception:
-            pass
+        if args.workload == "wildtrack":
+            try:  # DRAM traffic / pipe utilisation of the dominant kernel from the committed ncu --set full capture
+                with open(os.path.join(REPO, "profiles", "ncu_dominant_kernel.json")) as f:
+                    prof = json.load(f)
+            except Exception:
+                pass
         roofline["traffic"] = prof.get("dram_bytes_per_launch")
         roofline["traffic_source"] = prof.get("source")
         roofline["onchip_frac"] = prof.get("l1tex_data_pipe_frac")
-        roofline["onchip_note"] = ("the kernel's binding resource is the SM L1/shared-memory data pipe (4 corners x 64 B per "
-                                   "sample = 4.33 GB of on-chip gather per launch, >= 116 us at 128 B/clk/SM); onchip_frac "
-                                   "= l1tex data-pipe utilisation from the ncu capture")
-        cpu = cpu_baseline_leg() if world == 1 else None
+        roofline["onchip_note"] = ("the kernel's binding resource is the SM L1/shared-memory data pipe (4 corners x D x 4 "
+                                   "B per sample through a 128 B/clk/SM pipe; DESIGN.md 4.1); onchip_frac = l1tex "
+                                   "data-pipe utilisation from the ncu capture")
+        cpu = cpu_baseline_leg(args.workload) if world == 1 else None
+        rcf = None
+        if world == 1:
+            try:
+                with torch.no_grad():
+                    ours_out = fusion.fuse(feats_dev[0], projs_dev[0]).clone()
+                rcf = ref_cuda_frame(fusion, ds, wl, device, ours_out, feats_dev[0], projs_dev[0],
+                                     iters=10 if args.workload != "stress4k" else 3)
+                if "kernels_only" in rcf:
+                    rcf["ours_over_ref_kernels_only"] = value / rcf["kernels_only"]["frames_per_sec"]
+                    rcf["ours_over_ref_as_shipped"] = value / rcf["as_shipped"]["frames_per_sec"]
+            except Exception as e:  # comparator only; never fatal
+                rcf = {"error": repr(e)[:300]}
+        cfg = workload_config(wl, BN, feat_shape, ds.Rworld_shape)
+        cfg.update({"mode": mode, "cuda_graph": True, "tf32": False, "gemm": gemm_mode,
+                    "convs": "3x3 convs as im2col GEMMs (ours)" if fusion.gemm_path else "cuDNN fp32",
+                    "l2": "2 alternating frame slots; per-step working set ~1.5 GB >> 126 MB L2"})
         line = {"metric": "multiview_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": WORKLOAD, "views": BN, "feat": list(feat_shape),
-                           "world_grid": list(ds.Rworld_shape), "layers": LAYERS, "heads": HEADS, "points": POINTS,
-                           "mode": mode, "cuda_graph": True, "tf32": False,
-                           "gemm": gemm_mode,
-                           "convs": "3x3 convs as im2col GEMMs (ours)" if fusion.gemm_path else "cuDNN fp32",
-                           "l2": "2 alternating frame slots; per-step working set ~1.5 GB >> 126 MB L2"},
+                # one frame's work is split across the ranks (views) => total work fixed as N grows, at every N
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": cfg,
                 "roofline": roofline,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "pipeline": "pinned host -> H2D stream / graph replay / D2H stream, 2 slots"},
-                # ours per frame: transpose + warp, then per layer 1 fused MSDA + 2 add_layernorm (+ 2 bias_act when the
-                # Linear layers run through torch.mm instead of the cuBLASLt epilogues)
-                # (GEMM conv path: + upsample_im2col + the final NHWC->NCHW transpose)
-                "gpu_launches": (2 + (3 if lt and _ops._GEMM_MODE != "torch" else 5) * LAYERS +
-                                 (2 if fusion.gemm_path else 0)) * args.steps,
+                "gpu_launches": our_launches_per_frame(fusion, lt_gemm) * args.steps,
                 "clocks": clocks,
                 "hot_path": {"warp_us": wk["us"], "warp_kernel": wk.get("launches"), "msda_fused_fwd_us": dom["us"],
                              "frames_per_sec_kernels_only": 1e6 / hot_us,
-                             "warp_GBps": wk["GBps"], "warp_frac": wk["GBps"] / peak},
+                             "warp_algorithmic_bytes": wk["bytes"], "warp_GBps": wk["GBps"],
+                             "warp_frac": wk["GBps"] / peak,
+                             "warp_frac_note": "SURVEY 8(d) algorithmic bytes (source + warped grid once) / time of the "
+                                               "launch(es) the frame issues for the stage"},
                 "kernels": kb}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if rcf is not None:
+            line["ref_cuda_frame"] = rcf
     if line is not None:
         emit(line)
     if world > 1:
@@ -526,10 +643,14 @@ def main():
     os.dup2(2, 1)            # ... and send every other write to fd 1 (C libraries included) to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="default: 200 (ours), 20 (reference: ~1 s per CPU frame)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MVD_BENCH_WORKLOAD", "wildtrack"),
+                    choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 200 if args.impl == "ours" else 20
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

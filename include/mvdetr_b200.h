@@ -179,6 +179,20 @@ MVD_API int mvd_warp_fwd_f32(const float* src, const float* Mat,
                      int BN, int C, int Hi, int Wi, int Ho, int Wo,
                      float* dst, int layout, void* stream);
 
+/* The same warp as ONE launch on an NCHW source (the backbone's layout, ref: mvd/models/mvdetr.py:177-178): per destination
+ * tile the source bounding box is staged in shared memory by TMA (boxes of the 4-D NCHW tensor map, out-of-image
+ * coordinates zero-filled = the op's zero padding) and gathered from there; tiles whose bounding box does not fit take
+ * masked global loads in the same kernel. Bit-identical results to mvd_warp_fwd_f32 / mvd_warp_im2col_f32.
+ *   mode 0: dst [BN, C, Ho, Wo]   (kornia contract)           replaces kornia.warp_perspective, mvd/models/mvdetr.py:194-195
+ *   mode 1: dst [BN, Ho, Wo, C]   (skips the permute-copy of   ref: mvd/models/trans_world_feat.py:92)
+ *   mode 2: dst = im2col matrix [BN*Ho2*Wo2, 9*C] of the 3x3 / `stride` / pad-1 convolution over the warped grid
+ *           (stride in {1,2}; layout as mvd_warp_im2col_f32)    ref: mvd/models/trans_world_feat.py:74,89
+ * MVD_ERR_UNSUPPORTED unless C % 32 == 0 and Wi % 4 == 0 (callers then use mvd_warp_fwd_f32 / mvd_warp_im2col_f32);
+ * src and dst 16-byte aligned. */
+MVD_API int mvd_warp_tma_f32(const float* src, const float* Mat,
+                     int BN, int C, int Hi, int Wi, int Ho, int Wo,
+                     float* dst, int mode, int stride, void* stream);
+
 /* Backward of the warp w.r.t. `src` (the backbone trains through it, ref: mvd/models/mvdetr.py:177-195;
  * `Mat` carries no gradient in MVDeTr).  Replaces ATen grid_sampler_2d_backward as reached from kornia.
  *   grad_dst [BN, C, Ho, Wo]   grad_src [BN, C, Hi, Wi] zeroed by this call, then atomically accumulated. */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mvd_linear_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p],
     "mvd_bias_act_f32": [_p, _p, ctypes.c_int64, _i, _i, _p],
     "mvd_warp_fwd_f32": [_p, _p] + [_i] * 6 + [_p, _i, _p],
+    "mvd_warp_tma_f32": [_p, _p] + [_i] * 6 + [_p, _i, _i, _p],
     "mvd_warp_bwd_f32": [_p, _p] + [_i] * 6 + [_p, _p],
     "mvd_warp_bwd_nhwc_f32": [_p, _p] + [_i] * 6 + [_p, _p],
     "mvd_transpose_f32": [_p, _i, _i, _i, _p, _p],

@@ -43,7 +43,8 @@ struct LtApi {
                            void*, cublasLtMatrixLayout_t, const cublasLtMatmulAlgo_t*, void*, size_t,
                            cudaStream_t) = nullptr;
   size_t (*GetVersion)(void) = nullptr;
-  cublasLtHandle_t handle = nullptr;
+  cublasStatus_t (*Destroy)(cublasLtHandle_t) = nullptr;
+  cublasLtHandle_t handle = nullptr;  // handle of the device the CURRENT call runs on (see handle_for)
   bool ok = false;
 };
 
@@ -59,7 +60,18 @@ std::mutex g_mu;
 LtApi g_lt;
 bool g_lt_tried = false;
 // key: rows, K, N, epilogue flags (1 = bias, 2 = relu), precision, device
-std::map<std::tuple<int64_t, int, int, int, int, int>, Plan> g_plans;
+std::map<std::tuple<int64_t, int, int, int, int, int>, Plan> g_plans;  // invalid plans are cached too (negative result)
+std::map<int, cublasLtHandle_t> g_handles;                             // one cuBLASLt handle per device (context)
+
+// Lock held, library loaded. A cuBLASLt handle belongs to the context it was created in: one per device.
+cublasLtHandle_t handle_for(int dev) {
+  auto it = g_handles.find(dev);
+  if (it != g_handles.end()) return it->second;
+  cublasLtHandle_t h = nullptr;
+  if (g_lt.Create(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
+  g_handles[dev] = h;
+  return h;
+}
 
 template <typename F>
 bool sym(void* so, const char* name, F* out) {
@@ -89,7 +101,7 @@ bool load_lt() {
                      sym(so, "cublasLtMatmulPreferenceDestroy", &api.PrefDestroy) &&
                      sym(so, "cublasLtMatmulAlgoGetHeuristic", &api.Heuristic) &&
                      sym(so, "cublasLtMatmul", &api.Matmul) && sym(so, "cublasLtGetVersion", &api.GetVersion);
-    if (!all || api.GetVersion() < 120900 || api.Create(&api.handle) != CUBLAS_STATUS_SUCCESS) {
+    if (!all || api.GetVersion() < 120900) {
       dlclose(so);
       continue;
     }
@@ -221,16 +233,20 @@ extern "C" int mvd_linear_f32(const float* x, const float* W, const float* bias,
   MVD_CUDA_TRY(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_mu);
   if (!load_lt()) return MVD_ERR_NO_DEVICE;
+  g_lt.handle = handle_for(dev);
+  if (!g_lt.handle) return MVD_ERR_NO_DEVICE;
   const int epi = (bias ? 1 : 0) | (relu ? 2 : 0);
   const auto key = std::make_tuple(rows, K, N, epi, precision, dev);
   auto it = g_plans.find(key);
   if (it == g_plans.end()) {
     Plan p;
     const TuneArgs tune{W, x, out, workspace, workspace ? workspace_bytes : 0, (cudaStream_t)stream};
-    if (int e = make_plan(rows, K, N, epi, precision, bias, workspace ? workspace_bytes : 0, &p, &tune)) return e;
-    it = g_plans.emplace(key, p).first;
+    const int e = make_plan(rows, K, N, epi, precision, bias, workspace ? workspace_bytes : 0, &p, &tune);
+    if (e != MVD_OK && e != MVD_ERR_UNSUPPORTED) return e;
+    it = g_plans.emplace(key, p).first;  // p.valid == false records "no algorithm": the query is not repeated
   }
   Plan& p = it->second;
+  if (!p.valid) return MVD_ERR_UNSUPPORTED;
   if (p.workspace > (workspace ? workspace_bytes : 0)) return MVD_ERR_UNSUPPORTED;
   if (epi & 1) g_lt.DescSet(p.desc, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias));
   const float alpha = 1.f, beta = 0.f;

@@ -230,8 +230,8 @@ extern "C" int mvd_msda_bwd_viewgrid_f32(const float* grad_out, const float* val
   if (!grad_out || !value || !loc || !attn || !grad_value || !grad_loc || !grad_attn) return MVD_ERR_NULL_POINTER;
   if (B <= 0 || H <= 0 || W <= 0 || M <= 0 || D <= 0 || L <= 0 || R <= 0 || P <= 0) return MVD_ERR_BAD_SHAPE;
   if ((int64_t)B * L * H * W * M * D > 0x7fffffffLL || (int64_t)B * R * H * W * M * L * P * 2 > 0x7fffffffffLL)
-    return MVD_ERR_BAD_SHAPE;
-  if (M > 65535 || B > 65535) return MVD_ERR_BAD_SHAPE;
+    return MVD_ERR_UNSUPPORTED;  // generic kernel (64-bit indexing) takes the call
+  if (M > 65535 || B > 65535) return MVD_ERR_UNSUPPORTED;
   if (!((D == 8 || D == 16 || D == 32) && (P == 4 || P == 8))) return MVD_ERR_UNSUPPORTED;
   const uintptr_t al = reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(value) |
                        reinterpret_cast<uintptr_t>(loc) | reinterpret_cast<uintptr_t>(attn) |

@@ -300,9 +300,10 @@ int viewgrid_dispatch(const float* value, const float* loc, const float* attn, c
                       const float* off_bias, const float* logit_bias, int B, int H, int W, int M, int D, int L, int R,
                       int P, int Lr, float* out, cudaStream_t st) {
   if (B <= 0 || H <= 0 || W <= 0 || M <= 0 || D <= 0 || L <= 0 || R <= 0 || P <= 0) return MVD_ERR_BAD_SHAPE;
+  // beyond the 32-bit indexing of this kernel: not an error, the generic kernel (64-bit indexing) takes the call
   if ((int64_t)B * L * H * W * M * D > 0x7fffffffLL || (int64_t)B * R * H * W * M * L * P * 2 > 0x7fffffffffLL)
-    return MVD_ERR_BAD_SHAPE;
-  if (M > 65535 || B > 65535) return MVD_ERR_BAD_SHAPE;
+    return MVD_ERR_UNSUPPORTED;
+  if (M > 65535 || B > 65535) return MVD_ERR_UNSUPPORTED;
   if (!((D == 8 || D == 16 || D == 32) && (P == 4 || P == 8))) return MVD_ERR_UNSUPPORTED;
   if (FUSED && Lr != H * W) return MVD_ERR_UNSUPPORTED;  // table rows must be the grid cells (mvdetr.py:33-71)
   const uintptr_t al = reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(loc) |

@@ -56,6 +56,7 @@ __device__ __forceinline__ float linspace_pm1(int i, int n) {
 
 struct Taps {
   int o00;            // offset of the north-west tap inside one source plane (may be out of range; see masks)
+  int x0, y0;         // the north-west tap in source pixels (x0 in [-1, Wi-1], y0 in [-1, Hi-1] when any mask is set)
   float nw, ne, sw, se;
   bool m_nw, m_ne, m_sw, m_se;
 };
@@ -73,6 +74,7 @@ __device__ __forceinline__ Taps make_taps(const float* T, int u, int v, int Hi, 
   t.m_nw = t.m_ne = t.m_sw = t.m_se = false;
   t.nw = t.ne = t.sw = t.se = 0.f;
   t.o00 = 0;
+  t.x0 = t.y0 = 0;
   // also false for NaN coordinates
   if (ix > -1.f && iy > -1.f && ix < (float)Wi && iy < (float)Hi) {
     const float fx = floorf(ix), fy = floorf(iy);
@@ -89,6 +91,8 @@ __device__ __forceinline__ Taps make_taps(const float* T, int u, int v, int Hi, 
     t.m_sw = bot && lef;
     t.m_se = bot && rig;
     t.o00 = y0 * Wi + x0;
+    t.x0 = x0;
+    t.y0 = y0;
   }
   return t;
 }

@@ -77,18 +77,31 @@ class FrameRunner:
         self.compute = torch.cuda.Stream(device=device)
         self.s_in = torch.cuda.Stream(device=device)
         self.s_out = torch.cuda.Stream(device=device)
+        self.use_graph = use_graph
+        self.recapture()
+
+    def _param_versions(self):
+        return tuple((p.data_ptr(), p._version) for p in self.fusion.parameters())
+
+    def recapture(self):
+        """(Re)runs the warm-up and captures the CUDA graphs. The graphs bake in derived copies of some parameters (conv
+        weights in GEMM layout, position + level embedding); after load_state_dict() or any in-place weight update call
+        this again -- step() refuses to replay a graph captured from other parameter versions."""
+        depth, device = self.depth, self.device
+        self.graphs = [None] * depth
         with torch.no_grad():
             with torch.cuda.stream(self.compute):
                 for i in range(depth):
                     for _ in range(2):  # warm-up: cuDNN/cuBLAS heuristics, lazy buffers
                         self.out[i] = self.fusion.fuse(self.feat[i], self.proj[i])
                 self.compute.synchronize()
-                if use_graph:
+                if self.use_graph:
                     for i in range(depth):
                         g = torch.cuda.CUDAGraph()
                         with torch.cuda.graph(g, stream=self.compute):
                             self.out[i] = self.fusion.fuse(self.feat[i], self.proj[i])
                         self.graphs[i] = g
+        self._captured_versions = self._param_versions()
         torch.cuda.synchronize(device)
 
     def load(self, imgs_feat, proj_mats, slot=0):
@@ -99,6 +112,9 @@ class FrameRunner:
         """One frame on the inputs already in slot `slot`; asynchronous on self.compute; returns the output buffer."""
         with torch.cuda.stream(self.compute):
             if self.graphs[slot] is not None:
+                if self._param_versions() != self._captured_versions:
+                    raise RuntimeError("FrameRunner: model parameters changed since the CUDA graphs were captured "
+                                       "(load_state_dict / in-place update); call recapture() first")
                 self.graphs[slot].replay()
             else:
                 with torch.no_grad():

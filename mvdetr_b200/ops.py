@@ -24,6 +24,7 @@ from . import _C
 _VIEWGRID = os.environ.get("MVDETR_B200_VIEWGRID", "1") != "0"
 _BWD_VIEWGRID = os.environ.get("MVDETR_B200_BWD_VIEWGRID", "0") == "1"  # experimental TMA-staged backward (opt-in)
 _WARP_CL = os.environ.get("MVDETR_B200_WARP_CL", "1") != "0"  # 0: always the scalar NCHW-source warp kernels (A/B switch)
+_WARP_TMA = os.environ.get("MVDETR_B200_WARP_TMA", "1") != "0"  # 0: relayout + channels-last gather (round-1 path)
 
 
 def _stream(t):
@@ -89,6 +90,21 @@ def _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_loc, a
     return B, S, M, D, L, Lq, P
 
 
+_shape_cache = {}
+
+
+def _host_shapes(spatial_shapes):
+    """Host copy of the [L,2] int64 device tensor, cached per (storage, version): one device->host read the first time
+    a shapes tensor is seen, none afterwards (keeps the autograd path CUDA-graph capturable once warmed up)."""
+    key = (spatial_shapes.device, spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape))
+    got = _shape_cache.get(key)
+    if got is None:
+        if len(_shape_cache) > 64:
+            _shape_cache.clear()
+        got = _shape_cache[key] = spatial_shapes.tolist()
+    return got
+
+
 def _viewgrid_geometry(value, spatial_shapes, S, L, Lq):
     """Returns (H, W, R) when every level is the same HxW grid and the queries are R copies of that grid
     (MVDeTr's encoder layout), else None. Reads `spatial_shapes` back to the host (one small sync; the reference's
@@ -98,7 +114,7 @@ def _viewgrid_geometry(value, spatial_shapes, S, L, Lq):
     hw = S // L
     if Lq % hw != 0:
         return None
-    shapes = spatial_shapes.tolist()
+    shapes = _host_shapes(spatial_shapes)
     H, W = shapes[0]
     if H * W != hw or any(s != [H, W] for s in shapes):
         return None
@@ -284,6 +300,39 @@ def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None, perm_inner=0):
 _DST_NHWC, _SRC_NHWC = 1, 2  # MVD_WARP_* layout bits of include/mvdetr_b200.h
 
 
+def _tma_warp_ok(src):
+    """The one-launch TMA warp takes a plain NCHW source with C % 32 == 0 and Wi % 4 == 0 (16-byte row pitch)."""
+    return (_WARP_TMA and src.is_contiguous() and src.shape[1] % 32 == 0 and src.shape[3] % 4 == 0 and
+            src.data_ptr() % 16 == 0)
+
+
+def _warp_tma(src, mat, Ho, Wo, dst, mode, stride=1):
+    BN, C, Hi, Wi = src.shape
+    with _on_device(src):
+        rc = _C.lib.mvd_warp_tma_f32(src.data_ptr(), mat.data_ptr(), BN, C, Hi, Wi, Ho, Wo, dst.data_ptr(), mode,
+                                     int(stride), _stream(src))
+    if rc == -3:
+        return False
+    _C.check(rc, "mvd_warp_tma_f32")
+    return True
+
+
+def warp_launch_names(src, channels_last=False, im2col=False):
+    """Kernels one warp call launches for this source (bench.py reports it next to the timing)."""
+    if _tma_warp_ok(src):
+        return "warp_tma_kernel<%s> (1 launch)" % ("IM2COL" if im2col else "NHWC" if channels_last else "NCHW")
+    cl_src = src.is_contiguous(memory_format=torch.channels_last) and not src.is_contiguous()
+    pre = "" if cl_src else "mvd_transpose_f32 + "
+    if im2col:
+        return pre + "warp_im2col_kernel"
+    return pre + ("warp_fwd_cl_kernel<NHWC dst>" if channels_last else "warp_fwd_cl_kernel<NCHW dst>")
+
+
+def warp_launch_count(im2col=True):
+    """Launches of the warp stage per frame on an NCHW source (1 with the TMA kernel, else relayout + gather)."""
+    return 1 if _WARP_TMA else 2
+
+
 def warp_im2col(src, M, dsize, stride=2):
     """Perspective warp of src [BN,C,Hi,Wi] (as warp_perspective) written as the im2col matrix of a 3x3 / stride /
     pad-1 convolution over the warped grid: returns A [BN*Ho2*Wo2, 9*C] (token-major, taps (ky,kx,c)) and (Ho2, Wo2).
@@ -293,9 +342,11 @@ def warp_im2col(src, M, dsize, stride=2):
     if not (src.is_cuda and src.dtype == torch.float32 and C % 4 == 0):
         raise RuntimeError("warp_im2col: fp32 CUDA source with C % 4 == 0 required")
     mat = M.detach().to(device=src.device, dtype=torch.float32).contiguous()
-    src_cl, _ = _as_nhwc(src)
     Ho2, Wo2 = (Ho - 1) // stride + 1, (Wo - 1) // stride + 1
     A = torch.empty((BN * Ho2 * Wo2, 9 * C), dtype=src.dtype, device=src.device)
+    if _tma_warp_ok(src) and _warp_tma(src, mat, Ho, Wo, A, 2, stride):  # NCHW source: one launch, TMA-staged
+        return A, (Ho2, Wo2)
+    src_cl, _ = _as_nhwc(src)
     with _on_device(src):
         rc = _C.lib.mvd_warp_im2col_f32(src_cl.data_ptr(), mat.data_ptr(), BN, C, Hi, Wi, Ho, Wo, int(stride),
                                         A.data_ptr(), _stream(src))
@@ -349,8 +400,9 @@ def linear_available():
 def linear(x, weight, bias=None, relu=False, mode=None):
     """act(x @ weight.T + bias) for x [rows, K], weight [N, K] (nn.Linear layout), fp32 CUDA, through mvd_linear_f32.
     mode "bf16x9": fp32 emulated on the tensor cores (cuBLASLt 12.9 CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32-level
-    accuracy); "fp32": the same library's native fp32; "torch": torch.mm + our bias kernel. Falls back to "torch" when
-    the library or an algorithm is unavailable (returns the same values up to fp32 rounding)."""
+    accuracy); "fp32": the same library's native fp32; "torch": torch.mm + our bias kernel (explicit opt-in with
+    MVDETR_B200_GEMM=torch or mode="torch"). There is NO silent fallback: when the toolkit's cuBLASLt cannot be loaded
+    or has no algorithm for the request, this raises and names the switch."""
     mode = mode or _GEMM_MODE
     rows, K = x.shape
     N = weight.shape[0]
@@ -359,9 +411,11 @@ def linear(x, weight, bias=None, relu=False, mode=None):
         for name, t in (("x", x), ("weight", weight), ("bias", bias)):
             if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
                 raise RuntimeError(f"linear: {name} must be a contiguous fp32 CUDA tensor")
-        ws = _gemm_ws.get(x.device)
+        # scratch per (device, stream): two streams running GEMMs concurrently must not share it
+        ws_key = (x.device, _stream(x))
+        ws = _gemm_ws.get(ws_key)
         if ws is None:
-            ws = _gemm_ws[x.device] = torch.empty(64 << 20, dtype=torch.uint8, device=x.device)
+            ws = _gemm_ws[ws_key] = torch.empty(64 << 20, dtype=torch.uint8, device=x.device)
         out = torch.empty((rows, N), dtype=x.dtype, device=x.device)
         with _on_device(x):
             rc = _C.lib.mvd_linear_f32(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
@@ -369,14 +423,43 @@ def linear(x, weight, bias=None, relu=False, mode=None):
                                        ws.data_ptr(), ws.numel(), _stream(x))
         if rc == 0:
             return out
-        if rc not in (-3, -5):  # UNSUPPORTED / NO_DEVICE -> torch path
-            _C.check(rc, "mvd_linear_f32")
+        if rc in (-3, -5):
+            raise RuntimeError(
+                f"mvdetr_b200.linear: cuBLASLt >= 12.9 path unavailable ({_C.error_string(rc)}; rows={rows}, K={K}, "
+                f"N={N}, mode={mode}). Set MVDETR_B200_GEMM=torch to run the dense layers through torch.mm instead "
+                "(about 1.5x slower frames); it is never selected silently.")
+        _C.check(rc, "mvd_linear_f32")
     out = torch.mm(x, weight.t())
     if bias is not None and N % 4 == 0:
         return bias_act_(out, bias, relu=relu)
     if bias is not None:
         out = out + bias
     return torch.relu_(out) if relu else out
+
+
+def gemm_mode_text():
+    """One line describing how ops.linear runs (bench.py's config.gemm)."""
+    lt = linear_available()
+    if _GEMM_MODE == "torch":
+        return "torch.mm fp32 (cuBLAS SIMT), explicit MVDETR_B200_GEMM=torch"
+    if not lt:
+        return "UNAVAILABLE: cuBLASLt >= 12.9 not loadable (ops.linear raises)"
+    return (f"{_GEMM_MODE} via cuBLASLt {lt} (fp32 in/out; bf16x9 = CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32-accurate "
+            "tensor-core emulation)")
+
+
+def pos_add_launches(layers):
+    """Launches of the query = src + pos add per frame that are OURS (0: the adds are torch elementwise kernels)."""
+    return 0
+
+
+def msda_bwd_kernel_name(value, hw, Lq):
+    """Which backward kernel ms_deform_attn_backward dispatches for this layout (bench.py reports it)."""
+    B, S, M, D = value.shape
+    uniform = all(s == hw[0] for s in hw)
+    if _BWD_VIEWGRID and uniform and value.dtype == torch.float32 and D in (8, 16, 32):
+        return f"msda_vg_bwd_kernel<{D}> (TMA-staged view grid)"
+    return f"msda_bwd_vec4_kernel<{D}> (generic)" if D % 4 == 0 else "msda_bwd_scalar_kernel"
 
 
 def bias_act_(x, bias, relu=False):
@@ -405,6 +488,10 @@ class _WarpPerspective(Function):
         shape = (BN, Ho, Wo, C) if channels_last else (BN, C, Ho, Wo)
         dst = torch.empty(shape, dtype=src.dtype, device=src.device)
         vec = C % 4 == 0 and _WARP_CL
+        if vec and _tma_warp_ok(src) and _warp_tma(src, mat, Ho, Wo, dst, 1 if channels_last else 0):
+            ctx.save_for_backward(mat)
+            ctx.geom = (BN, C, Hi, Wi, Ho, Wo, channels_last, vec)
+            return dst
         layout = _DST_NHWC if channels_last else 0
         if vec:
             src, _ = _as_nhwc(src)

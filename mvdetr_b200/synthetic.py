@@ -7,6 +7,7 @@ on the boxes). The objects returned expose exactly the attributes the reference 
 
   wildtrack_like()   7 cameras, 1080p, 480x1440 grid of 2.5 cm cells, ij indexing   ref: datasets/Wildtrack.py:21-32
   multiviewx_like()  6 cameras, 1080p, 640x1000 grid of 2.5 cm cells (metres), xy   ref: datasets/MultiviewX.py:21-32
+  stress4k_like()    8 cameras, 2160x3840, 960x2880 grid of 2.5 cm cells (BASELINE configs[3])
   mini_scene()       the small 3-camera scene behind tests/golden/world_feat_mini.npz
 """
 import types
@@ -72,6 +73,15 @@ def multiviewx_like(seed=0, world_reduce=4, img_reduce=12):
     grid = [[0.025, 0, 0], [0, 0.025, 0], [0, 0, 1]]
     return ring_scene(6, (640 // world_reduce, 1000 // world_reduce), (1080 // img_reduce, 1920 // img_reduce),
                       world_reduce, img_reduce, grid, "xy", 1.0, focal_px=1750.0, height_range=(2.0, 4.0),
+                      radius_scale=0.75, seed=seed)
+
+
+def stress4k_like(seed=0, world_reduce=4, img_reduce=12):
+    """8 x 4K views, Rimg 180x320, Rworld 240x720: the "8-view 4K, C=256, K=8" stress shape (the model on top uses
+    hidden 256, 8 heads of D=32, 8 points)."""
+    grid = [[0, 2.5, -600], [2.5, 0, -1800], [0, 0, 1]]
+    return ring_scene(8, (960 // world_reduce, 2880 // world_reduce), (2160 // img_reduce, 3840 // img_reduce),
+                      world_reduce, img_reduce, grid, "ij", 0.01, focal_px=3500.0, height_range=(300.0, 600.0),
                       radius_scale=0.75, seed=seed)
 
 

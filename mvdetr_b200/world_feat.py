@@ -108,8 +108,10 @@ class MSDeformAttn(nn.Module):
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
         M, L, P = self.n_heads, self.n_levels, self.n_points
 
+        # the fused kernels are instantiated for power-of-two head dims; any other D (e.g. hidden 192 / 8 heads = 24)
+        # takes the reference's own arithmetic below through the 6-argument op, which accepts every D
         fused = (ref_table is not None and not torch.is_grad_enabled() and input_flatten.dtype == torch.float32 and
-                 input_flatten.is_cuda)
+                 input_flatten.is_cuda and (self.d_model // self.n_heads) in (4, 8, 16, 32, 64, 128))
         if fused:
             value = ops.linear(input_flatten.reshape(N * Len_in, -1), self.value_proj.weight, self.value_proj.bias)
         else:
@@ -171,7 +173,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
         """perm_inner > 0 (inference fast path only): the layer's output rows leave cell-major, see add_layer_norm."""
         fast = (not torch.is_grad_enabled() and not self.training and src.is_cuda and src.dtype == torch.float32
                 and src.shape[-1] % 4 == 0 and src.shape[-1] <= 1024)
-        defer = fast and ref_table is not None
+        defer = fast and ref_table is not None and (src.shape[-1] // self.self_attn.n_heads) in (4, 8, 16, 32, 64, 128)
         src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                               level_start_index, padding_mask, geometry=geometry, ref_table=ref_table,
                               ref_table_lm=ref_table_lm, defer_output_bias=defer)

@@ -71,11 +71,18 @@ def warp_perspective(src, mat, dsize):
     return F.grid_sample(src, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
 
 
-def msda_module_forward(sd, prefix, query, ref_points, src, shapes, n_heads, n_points):
+def msda_module_forward(sd, prefix, query, ref_points, src, shapes, n_heads, n_points, msda_fn=None,
+                        shapes_dev=None):
     """MSDeformAttn.forward with per-(level, point) reference points [B,Lq,L,P,2] (MVDeTr's modification,
-    ms_deform_attn.py:104-107). sd: state_dict, prefix e.g. 'encoder.layers.0.self_attn.'."""
+    ms_deform_attn.py:104-107). sd: state_dict, prefix e.g. 'encoder.layers.0.self_attn.'.
+    msda_fn(value, shapes_dev, start_dev, loc, attn): replaces msda_core (bench.py plugs the reference's own CUDA op
+    in here); shapes_dev = ([L,2] int64 spatial_shapes, [L] level_start_index, sync) on the device as the reference's
+    caller builds them (trans_world_feat.py:95-96); sync=True reproduces its device->host assert
+    (ms_deform_attn.py:94)."""
     B, Lq, C = query.shape
     L = len(shapes)
+    if shapes_dev is not None and shapes_dev[2]:
+        assert (shapes_dev[0][:, 0] * shapes_dev[0][:, 1]).sum() == src.shape[1]
     value = F.linear(src, sd[prefix + "value_proj.weight"], sd[prefix + "value_proj.bias"])
     value = value.view(B, src.shape[1], n_heads, C // n_heads)
     off = F.linear(query, sd[prefix + "sampling_offsets.weight"], sd[prefix + "sampling_offsets.bias"])
@@ -84,14 +91,18 @@ def msda_module_forward(sd, prefix, query, ref_points, src, shapes, n_heads, n_p
     aw = F.softmax(aw.view(B, Lq, n_heads, L * n_points), -1).view(B, Lq, n_heads, L, n_points)
     norm = torch.tensor([[w, h] for h, w in shapes], dtype=query.dtype, device=query.device)
     loc = ref_points[:, :, None] + off / norm[None, None, None, :, None, :]
-    out = msda_core(value, shapes, loc, aw)
+    if msda_fn is not None:
+        out = msda_fn(value, shapes_dev[0], shapes_dev[1], loc, aw)
+    else:
+        out = msda_core(value, shapes, loc, aw)
     return F.linear(out, sd[prefix + "output_proj.weight"], sd[prefix + "output_proj.bias"])
 
 
-def encoder_layer_forward(sd, prefix, src, pos, ref_points, shapes, n_heads, n_points):
+def encoder_layer_forward(sd, prefix, src, pos, ref_points, shapes, n_heads, n_points, msda_fn=None, shapes_dev=None):
     """Eval-mode (dropout = identity) DeformableTransformerEncoderLayer.forward."""
     C = src.shape[-1]
-    a = msda_module_forward(sd, prefix + "self_attn.", src + pos, ref_points, src, shapes, n_heads, n_points)
+    a = msda_module_forward(sd, prefix + "self_attn.", src + pos, ref_points, src, shapes, n_heads, n_points,
+                            msda_fn, shapes_dev)
     src = F.layer_norm(src + a, (C,), sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"])
     f = F.linear(F.relu(F.linear(src, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])),
                  sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
@@ -114,21 +125,32 @@ def sine_pos_embedding(hw, num_pos_feats, temperature=10000.0):
     return torch.cat((py, px), dim=3).permute(0, 3, 1, 2)
 
 
-def world_feat_forward(sd, x, ref_points, n_heads=8, n_points=4, n_layers=3, stride=2):
+def world_feat_forward(sd, x, ref_points, n_heads=8, n_points=4, n_layers=3, stride=2, pos_embedding=None,
+                       msda_fn=None, sync_assert=False):
     """DeformTransWorldFeat.forward (eval mode) over state_dict `sd` (reference key names, no prefix).
-    x [1,N,C,H,W]; ref_points [N*Hd*Wd, N, P, 2]."""
+    x [1,N,C,H,W]; ref_points [N*Hd*Wd, N, P, 2].
+    As in the reference, `pos_embedding` [1,C,Hd,Wd] (built once; trans_world_feat.py:78) and `ref_points` are moved
+    to x.device on EVERY call (trans_world_feat.py:93, deformable_transformer.py:48): hand in host tensors to time
+    the path as shipped, device tensors to time its kernels only. sync_assert reproduces ms_deform_attn.py:94."""
     B, N, C, H, W = x.shape
     y = F.relu(F.conv2d(x.view(B * N, C, H, W), sd["downsample.0.weight"], sd["downsample.0.bias"], stride=stride,
                         padding=1))
     Cd, Hd, Wd = y.shape[1:]
     src = y.view(B, N, Cd, Hd, Wd).permute(0, 1, 3, 4, 2).reshape(B, N * Hd * Wd, Cd)
-    pos = sine_pos_embedding((Hd, Wd), Cd // 2).flatten(2).transpose(1, 2).unsqueeze(1)  # [1,1,HW,C]
+    if pos_embedding is None:
+        pos_embedding = sine_pos_embedding((Hd, Wd), Cd // 2)
+    pos = pos_embedding.to(x.device).flatten(2).transpose(1, 2).unsqueeze(1)  # [1,1,HW,C]
     pos = (pos + sd["lvl_embedding"].view(B, N, 1, Cd)).reshape(B, N * Hd * Wd, Cd)
     shapes = [(Hd, Wd)] * N
-    ref = ref_points.unsqueeze(0).expand(B, -1, -1, -1, -1)
+    shapes_dev = None
+    if msda_fn is not None or sync_assert:
+        sh = torch.as_tensor(shapes, dtype=torch.long, device=x.device)
+        shapes_dev = (sh, torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1])), sync_assert)
+    ref = ref_points.unsqueeze(0).repeat([B, 1, 1, 1, 1]).to(x.device)
     out = src
     for i in range(n_layers):
-        out = encoder_layer_forward(sd, f"encoder.layers.{i}.", out, pos, ref, shapes, n_heads, n_points)
+        out = encoder_layer_forward(sd, f"encoder.layers.{i}.", out, pos, ref, shapes, n_heads, n_points, msda_fn,
+                                    shapes_dev)
     mem = out.view(B, N, Hd, Wd, Cd).permute(0, 1, 4, 2, 3).reshape(B, N * Cd, Hd, Wd)
     merged = F.relu(F.conv2d(mem, sd["merge_linear.0.weight"], sd["merge_linear.0.bias"]))
     up = F.interpolate(merged, size=(H, W), mode="bilinear", align_corners=False)

@@ -26,11 +26,46 @@ def test_shim_modules_expose_the_reference_names():
     import importlib
     import sys
     shims = mvdetr_b200.install_shims()
-    assert sys.path[0] == shims
+    assert shims in sys.path[:2]
     msda = importlib.import_module("MultiScaleDeformableAttention")
     assert callable(msda.ms_deform_attn_forward) and callable(msda.ms_deform_attn_backward)
-    kornia = importlib.import_module("kornia")
-    assert kornia.warp_perspective is ops.warp_perspective
+    kornia = importlib.import_module("kornia")  # no real kornia in this image: the stub package
+    assert kornia.warp_perspective is ops.warp_perspective and kornia.__mvdetr_b200_stub__
+
+
+def test_a_real_kornia_is_wrapped_not_shadowed(tmp_path):
+    """with a real kornia installed, install_shims() must leave it importable and only route the hot-path
+    call (fp32 CUDA, bilinear / zeros / align_corners=False) to our kernel; e.g. the reference's dataset calls
+    kornia.warp_perspective(masks_cpu, M, size, 'nearest', align_corners=False) (frameDataset.py:80)."""
+    import os
+    import subprocess
+    import sys
+    pkg = tmp_path / "kornia"
+    pkg.mkdir()
+    (pkg / "__init__.py").write_text(
+        "calls = []\n"
+        "def warp_perspective(src, M, dsize, mode='bilinear', padding_mode='zeros', align_corners=None):\n"
+        "    calls.append((mode, align_corners))\n"
+        "    return 'real-kornia'\n"
+        "def other():\n    return 'untouched'\n")
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {str(tmp_path)!r})\n"
+        "import mvdetr_b200\n"
+        "mvdetr_b200.install_shims()\n"
+        "import kornia\n"
+        "assert not hasattr(kornia, '__mvdetr_b200_stub__') and kornia.other() == 'untouched'\n"
+        "src, M = torch.zeros(1, 1, 4, 4), torch.eye(3)[None]\n"
+        "assert kornia.warp_perspective(src, M, (4, 4), 'nearest', align_corners=False) == 'real-kornia'\n"
+        "assert kornia.warp_perspective(src, M, (4, 4), align_corners=False) == 'real-kornia'  # CPU tensor\n"
+        "assert kornia.calls == [('nearest', False), ('bilinear', False)]\n"
+        "assert kornia.warp_perspective.__mvdetr_b200_wrapped__\n"
+        "mvdetr_b200.install_shims()  # idempotent\n"
+        "assert kornia.warp_perspective.__wrapped__.__module__ == 'kornia'\n"
+        "print('OK')\n")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=repo)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
 
 
 def test_warp_argument_errors():

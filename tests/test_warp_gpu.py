@@ -190,3 +190,71 @@ def test_upsample_im2col_matches_interpolate_then_unfold(cuda, C, Hi, Wi, Ho, Wo
     A = ops.upsample_im2col(x.permute(0, 2, 3, 1).contiguous(), (Ho, Wo))
     assert A.shape == want.shape
     assert (A - want).abs().max().item() <= 1e-6
+
+
+def _tma_cases():
+    """(C, Hi, Wi, Ho, Wo, homography kind): geometries that exercise every branch of the TMA kernel."""
+    return [(32, 90, 160, 120, 360, "ring"),       # Wildtrack geometry, one 32-channel group
+            (128, 24, 32, 40, 72, "ring"),         # several groups per stage
+            (64, 128, 128, 16, 16, "shrink"),      # strong minification: bounding box > 64 px -> global-load path
+            (64, 16, 16, 70, 90, "zoom"),          # strong magnification: 1-2 source pixels per tile
+            (96, 20, 28, 33, 47, "outside"),       # image lands mostly / entirely outside: empty tiles write zeros
+            (32, 12, 16, 5, 7, "ring")]            # destination smaller than one tile
+
+
+def _homographies(kind, n, Hi, Wi, Ho, Wo, seed):
+    if kind == "ring":
+        return _ring_homographies(n, Hi, Wi, Ho, Wo, seed)
+    rng = np.random.RandomState(seed)
+    mats = []
+    for i in range(n):
+        if kind == "shrink":   # whole source onto the small destination
+            A = np.array([[Wo / Wi, 0.02, 0.3], [-0.01, Ho / Hi, 0.2], [1e-5, 2e-5, 1.0]])
+        elif kind == "zoom":   # a few source pixels cover the destination
+            A = np.array([[Wo / 3.0, 0.0, -Wo * (1 + i)], [0.0, Ho / 2.5, -Ho * 2.0], [0.0, 0.0, 1.0]])
+        else:                  # "outside": view 0 far away from the destination, others straddle its border
+            sh = [5.0, 0.6, -0.7][i % 3]
+            A = np.array([[Wo / Wi, 0.0, sh * Wo], [0.0, Ho / Hi, sh * Ho], [0.0, 0.0, 1.0]])
+        mats.append(A * rng.uniform(0.01, 2.0))
+    return np.stack(mats).astype(np.float32)
+
+
+@pytest.mark.parametrize("C,Hi,Wi,Ho,Wo,kind", _tma_cases())
+def test_tma_warp_kernel_every_mode(cuda, C, Hi, Wi, Ho, Wo, kind):
+    """The one-launch TMA-staged warp (NCHW source) in its three destination modes: bit-identical to the round-1
+    kernels (relayout + channels-last gather) and within 1e-4 of the C oracle."""
+    rng = np.random.RandomState(C + Ho)
+    src = rng.randn(3, C, Hi, Wi).astype(np.float32)
+    mats = _homographies(kind, 3, Hi, Wi, Ho, Wo, seed=C + Wo)
+    ref = co.warp_forward(src, mats, (Ho, Wo))
+    d_src, d_mats = dev(src, cuda), dev(mats, cuda)
+    assert ops._tma_warp_ok(d_src)
+    res = {}
+    for tma in (True, False):
+        old = ops._WARP_TMA
+        try:
+            ops._WARP_TMA = tma
+            res[tma] = (ops.warp_perspective(d_src, d_mats, (Ho, Wo), align_corners=False),
+                        ops.warp_perspective(d_src, d_mats, (Ho, Wo), align_corners=False, channels_last=True),
+                        ops.warp_im2col(d_src, d_mats, (Ho, Wo), stride=2)[0],
+                        ops.warp_im2col(d_src, d_mats, (Ho, Wo), stride=1)[0])
+        finally:
+            ops._WARP_TMA = old
+    assert np.abs(res[True][0].cpu().numpy() - ref).max() <= ATOL
+    if kind in ("ring", "shrink", "zoom"):
+        assert (ref != 0).any()
+    for a, b, what in zip(res[True], res[False], ("nchw", "nhwc", "im2col s2", "im2col s1")):
+        assert a.shape == b.shape and torch.equal(a, b), what
+    # Inf / NaN in parts of the source that no valid tap reads must not leak (zero weights are never multiplied in)
+    src2 = src.copy()
+    src2[:, :, 0, 0] = np.inf
+    o_tma = ops.warp_perspective(dev(src2, cuda), d_mats, (Ho, Wo), align_corners=False)
+    old = ops._WARP_TMA
+    try:
+        ops._WARP_TMA = False
+        o_old = ops.warp_perspective(dev(src2, cuda), d_mats, (Ho, Wo), align_corners=False)
+    finally:
+        ops._WARP_TMA = old
+    assert torch.equal(torch.isfinite(o_tma), torch.isfinite(o_old))
+    fin = torch.isfinite(o_old)
+    assert torch.equal(o_tma[fin], o_old[fin])
