@@ -251,6 +251,48 @@ MVD_API int mvd_warp_im2col_f32(const float* src, const float* Mat, int BN, int 
 MVD_API int mvd_upsample_im2col_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, float* A, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input side of the path: decoded camera frames -> normalised, resized network input in one kernel.
+ *   replaces T.Compose([T.ToTensor(), T.Normalize(mean, std), T.Resize((Ho, Wo))])   ref: mvd/datasets/frameDataset.py:66-67
+ *   img [N, Hi, Wi, 3] uint8 (HWC, as decoded)  ->  out [N, 3, Ho, Wo] fp32, out[n,c] = resize(((img/255) - mean[c]) / std[c])
+ *   mean_host / std_host: 3 floats each in HOST memory (read during the call).
+ *   antialias != 0: torchvision >= 0.17's behaviour on tensors, F.interpolate(bilinear, antialias=True) = ATen
+ *   _upsample_bilinear2d_aa (triangle filter of support Hi/Ho when down-scaling, normalised weights, separable);
+ *   antialias == 0: plain bilinear, align_corners=False. MVD_ERR_UNSUPPORTED for antialiased down-scaling beyond 7.5x.
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_resize_normalize_u8(const unsigned char* img, int N, int Hi, int Wi, int Ho, int Wo,
+                            const float* mean_host, const float* std_host, int antialias, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Output side of the path: ground-plane heatmap -> detections on the GPU, so that only the kept
+ * detections cross to the host (the reference copies both maps to the CPU and loops in Python).
+ *   mvd_decode_candidates_f32: for every cell with sigmoid(heatmap) > cls_thres writes (in arrival order)
+ *       cand_cell  [B, cap]     row-major cell number y*W + x
+ *       cand_pos   [B, cap, 2]  ((x + off_x) * reduce, (y + off_y) * reduce), swapped to (row, col) when swap_xy != 0
+ *                               (offset NULL: + 0.5 instead); each operation rounded separately, as torch does
+ *       cand_score [B, cap]     sigmoid(heatmap)
+ *       cand_count [B]          number of such cells (zeroed by the call; may exceed cap: the excess is dropped,
+ *                               cap = H*W can never overflow)
+ *     heatmap [B, 1, H, W] logits, offset [B, 2, H, W] (x, y) or NULL.
+ *     replaces mvdet_decode(torch.sigmoid(world_heatmap), world_offset, reduce)  ref: mvd/utils/decode.py:80-93
+ *              + `ids = scores > cls_thres; pos, s = positions[b, ids], scores[b, ids, 0]`  ref: mvd/trainer.py:121-133
+ *   mvd_distance_nms_f32: per batch element, reorders the candidates into row-major cell order (out_cell / out_pos /
+ *     out_score [B, cap(,2)]: the arrays the reference's boolean mask produces) and runs greedy distance NMS over
+ *     them: visit by descending score (ties: larger candidate number first), keep, drop every other candidate whose
+ *     distance to it is not > dist_thres; only the top_k best take part (top_k <= 0: all).
+ *       keep [B, cap] candidate numbers in the order kept, keep_count [B]
+ *     workspace: device scratch of mvd_distance_nms_workspace_bytes(B, cap) bytes, 8-byte aligned.
+ *     replaces nms(pos, s, 20, np.inf)   ref: mvd/utils/nms.py:7-44, call site mvd/trainer.py:134
+ * ------------------------------------------------------------------------------------------ */
+MVD_API size_t mvd_distance_nms_workspace_bytes(int B, int cap);
+MVD_API int mvd_decode_candidates_f32(const float* heatmap, const float* offset, int B, int H, int W, float reduce,
+                              float cls_thres, int swap_xy, int cap, int* cand_count, int* cand_cell,
+                              float* cand_pos, float* cand_score, void* stream);
+MVD_API int mvd_distance_nms_f32(const int* cand_count, const int* cand_cell, const float* cand_pos,
+                         const float* cand_score, int B, int cap, float dist_thres, int top_k,
+                         void* workspace, size_t workspace_bytes, int* out_cell, float* out_pos,
+                         float* out_score, int* keep, int* keep_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Linear layer out[rows, N] = act(x[rows, K] @ W[N, K]^T + bias[N]) through the CUDA toolkit's cuBLASLt (>= 12.9, loaded
  * by absolute path at first use: /usr/local/cuda/lib64/libcublasLt.so.12 or $MVD_CUBLASLT). Library GEMM, not a kernel
  * of ours; what it buys on B200 is `precision` = 1: CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32 operands split into three

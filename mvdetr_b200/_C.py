@@ -33,6 +33,10 @@ SIGNATURES = {
     "mvd_add_layernorm_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p],
     "mvd_warp_im2col_f32": [_p, _p] + [_i] * 7 + [_p, _p],
     "mvd_upsample_im2col_f32": [_p] + [_i] * 6 + [_p, _p],
+    "mvd_resize_normalize_u8": [_p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
+    "mvd_distance_nms_workspace_bytes": [_i, _i],
+    "mvd_decode_candidates_f32": [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _i, _i, _p, _p, _p, _p, _p],
+    "mvd_distance_nms_f32": [_p, _p, _p, _p, _i, _i, ctypes.c_float, _i, _p, ctypes.c_size_t, _p, _p, _p, _p, _p, _p],
     "mvd_linear_available": [],
     "mvd_linear_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p],
     "mvd_bias_act_f32": [_p, _p, ctypes.c_int64, _i, _i, _p],
@@ -48,7 +52,8 @@ SIGNATURES = {
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
-    _fn.restype = ctypes.c_char_p if _name == "mvd_error_string" else ctypes.c_int
+    _fn.restype = (ctypes.c_char_p if _name == "mvd_error_string" else
+                   ctypes.c_size_t if _name.endswith("_bytes") else ctypes.c_int)
 
 
 def error_string(code):

@@ -94,8 +94,14 @@ __global__ void __launch_bounds__(kWtThreads, 2)
   {
     constexpr unsigned FULL = 0xffffffffu;
     const int big = 0x7fffffff;
-    const int xl = __reduce_min_sync(FULL, valid ? x0 : big), yl = __reduce_min_sync(FULL, valid ? y0 : big);
-    const int xh = __reduce_max_sync(FULL, valid ? x0 + 1 : -big), yh = __reduce_max_sync(FULL, valid ? y0 + 1 : -big);
+    int xl = valid ? x0 : big, yl = valid ? y0 : big, xh = valid ? x0 + 1 : -big, yh = valid ? y0 + 1 : -big;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      xl = min(xl, __shfl_xor_sync(FULL, xl, d));
+      yl = min(yl, __shfl_xor_sync(FULL, yl, d));
+      xh = max(xh, __shfl_xor_sync(FULL, xh, d));
+      yh = max(yh, __shfl_xor_sync(FULL, yh, d));
+    }
     if (lane == 0 && xl != big) {
       atomicMin(&s_box[0], xl);
       atomicMin(&s_box[1], yl);
@@ -114,7 +120,6 @@ __global__ void __launch_bounds__(kWtThreads, 2)
   const int nsub = C / kWtCC;
   const int sps = staged ? min(nsub, kWtStageFloats / sub_floats) : 1;  // 32-channel groups per stage
   const int nchunks = (nsub + sps - 1) / sps;
-  const CUtensorMap* tm = bw == 16 ? &tm16 : (bw == 32 ? &tm32 : &tm64);
 
   auto issue_chunk = [&](int ch) {  // one thread: 32-channel groups [ch*sps, ...) -> stage ch & 1
     const int k0 = ch * sps, k1 = min(nsub, k0 + sps);
@@ -123,8 +128,13 @@ __global__ void __launch_bounds__(kWtThreads, 2)
     const uint32_t box_bytes = (uint32_t)(bw * kWtRows * kWtCC * 4);
     mbar_expect_tx(bar, (uint32_t)(k1 - k0) * (uint32_t)hg * box_bytes);
     for (int k = k0; k < k1; ++k)
-      for (int g = 0; g < hg; ++g)
-        tma_load_4d(st + (uint32_t)((k - k0) * hg + g) * box_bytes, tm, bar, xmin, ymin + g * kWtRows, k * kWtCC, n);
+      for (int g = 0; g < hg; ++g) {
+        const uint32_t dst = st + (uint32_t)((k - k0) * hg + g) * box_bytes;
+        // the tensor map operand is a kernel parameter named in the instruction (no computed descriptor address)
+        if (bw == 16) tma_load_4d(dst, &tm16, bar, xmin, ymin + g * kWtRows, k * kWtCC, n);
+        else if (bw == 32) tma_load_4d(dst, &tm32, bar, xmin, ymin + g * kWtRows, k * kWtCC, n);
+        else tma_load_4d(dst, &tm64, bar, xmin, ymin + g * kWtRows, k * kWtCC, n);
+      }
   };
   if (staged && tid == 0) {
     issue_chunk(0);

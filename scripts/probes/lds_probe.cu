@@ -14,20 +14,25 @@ __global__ void probe(const int* __restrict__ offs, long long* cyc, float* sink,
   __syncthreads();
   int o = offs[threadIdx.x & 31];  // byte offset for this lane
   float acc = 0.f;
+  const unsigned base = (unsigned)__cvta_generic_to_shared(sm);
   const long long t0 = clock64();
 #pragma unroll 8
   for (int it = 0; it < kIters; ++it) {
-    const char* p = reinterpret_cast<const char*>(sm) + o;
+    const unsigned a = base + (unsigned)o;  // asm volatile: the loads are neither hoisted nor merged
     if (WIDTH == 16) {
-      const float4 v = *reinterpret_cast<const float4*>(p);
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
       acc += v.x + v.y + v.z + v.w;
     } else if (WIDTH == 8) {
-      const float2 v = *reinterpret_cast<const float2*>(p);
+      float2 v;
+      asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
       acc += v.x + v.y;
     } else {
-      acc += *reinterpret_cast<const float*>(p);
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+      acc += v;
     }
-    o ^= (it & 1) ? 2048 : 4096;  // keep the loads from being hoisted; same pattern, different base
+    o ^= (it & 1) ? 2048 : 4096;  // same pattern, different base
   }
   const long long t1 = clock64();
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
