@@ -249,6 +249,10 @@ MVD_API int mvd_bias_act_f32(float* x, const float* bias, int64_t rows, int C, i
 MVD_API int mvd_warp_im2col_f32(const float* src, const float* Mat, int BN, int C, int Hi, int Wi, int Ho, int Wo,
                         int stride, float* A, void* stream);
 MVD_API int mvd_upsample_im2col_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, float* A, void* stream);
+/* Same, rows [row0, row0 + nrows) of the upsampled grid only: A [BN*nrows*Wo, 9*C] (row-sharded tail of the multi-GPU
+ * path: every rank convolves its own band of ground-plane rows; the band's halo rows are computed, not exchanged). */
+MVD_API int mvd_upsample_im2col_rows_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, int row0,
+                                 int nrows, float* A, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Input side of the path: decoded camera frames -> normalised, resized network input in one kernel.

@@ -33,6 +33,7 @@ SIGNATURES = {
     "mvd_add_layernorm_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p],
     "mvd_warp_im2col_f32": [_p, _p] + [_i] * 7 + [_p, _p],
     "mvd_upsample_im2col_f32": [_p] + [_i] * 6 + [_p, _p],
+    "mvd_upsample_im2col_rows_f32": [_p] + [_i] * 8 + [_p, _p],
     "mvd_resize_normalize_u8": [_p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p],
     "mvd_distance_nms_workspace_bytes": [_i, _i],
     "mvd_decode_candidates_f32": [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _i, _i, _p, _p, _p, _p, _p],

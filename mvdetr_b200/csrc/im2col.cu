@@ -23,14 +23,17 @@ constexpr int kImThreads = 128, kImPix = 32;
 
 // Stores the C-vector chunk `acc` (channels c .. c+3 of padded pixel (vp, up), vp/up = pixel + 1) into every im2col
 // slot that reads it. Token (oy, ox) tap (ky, kx) reads pixel (oy*s + ky - 1, ox*s + kx - 1).
+// Only token rows [row0, row1) are written, at row index oy - row0 (row-sharded callers; the whole grid is row0 = 0, row1 = Ho2).
 __device__ __forceinline__ void scatter_slots(float* __restrict__ A, const float4& acc, int vp, int up, int c, int C,
-                                              int s, int Ho2, int Wo2, int64_t token0) {
+                                              int s, int Ho2, int Wo2, int64_t token0, int row0 = 0,
+                                              int row1 = 0x7fffffff) {
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int ty = vp - ky;
     if (ty < 0 || ty % s != 0) continue;
-    const int oy = ty / s;
-    if (oy >= Ho2) continue;
+    int oy = ty / s;
+    if (oy >= Ho2 || oy < row0 || oy >= row1) continue;
+    oy -= row0;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int tx = up - kx;
@@ -115,15 +118,18 @@ __device__ __forceinline__ UpTap up_tap(int dst, float scale, int in_size) {
   return t;
 }
 
+// Rows [row0, row0 + nrows) of the upsampled grid only (nrows = Ho, row0 = 0: the whole grid): the block index walks
+// the padded pixel rows [row0 - 1, row0 + nrows] that feed those tokens.
 __global__ void __launch_bounds__(kImThreads) upsample_im2col_kernel(const float* __restrict__ src, int C, int Hi,
                                                                      int Wi, int Ho, int Wo, float scale_h,
-                                                                     float scale_w, float* __restrict__ A) {
+                                                                     float scale_w, int row0, int nrows,
+                                                                     float* __restrict__ A) {
   const int n = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int Wp = Wo + 2, npix = (Ho + 2) * Wp;
+  const int Wp = Wo + 2, npix = (nrows + 2) * Wp;
   const int pix0 = blockIdx.x * kImPix;
   const float* sbase = src + (int64_t)n * Hi * Wi * C;
-  const int64_t token0 = (int64_t)n * Ho * Wo;
+  const int64_t token0 = (int64_t)n * nrows * Wo;
   for (int c0 = 0; c0 < C; c0 += 128) {
     const int c = c0 + lane * 4;
     if (c >= C) continue;
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(kImThreads) upsample_im2col_kernel(const float
     for (int jj = 0; jj < kImPix / 4; ++jj) {
       const int pj = pix0 + warp * (kImPix / 4) + jj;
       if (pj >= npix) break;
-      const int vp = pj / Wp, up = pj - vp * Wp;
+      const int vp = pj / Wp + row0, up = pj - (pj / Wp) * Wp;  // padded coordinates in the FULL grid
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (vp >= 1 && vp <= Ho && up >= 1 && up <= Wo) {
         const UpTap ty = up_tap(vp - 1, scale_h, Hi), tx = up_tap(up - 1, scale_w, Wi);
@@ -145,7 +151,7 @@ __global__ void __launch_bounds__(kImThreads) upsample_im2col_kernel(const float
         acc.z = ty.l0 * (tx.l0 * v00.z + tx.l1 * v01.z) + ty.l1 * (tx.l0 * v10.z + tx.l1 * v11.z);
         acc.w = ty.l0 * (tx.l0 * v00.w + tx.l1 * v01.w) + ty.l1 * (tx.l0 * v10.w + tx.l1 * v11.w);
       }
-      scatter_slots(A, acc, vp, up, c, C, 1, Ho, Wo, token0);
+      scatter_slots(A, acc, vp, up, c, C, 1, Ho, Wo, token0, row0, row0 + nrows);
     }
   }
 }
@@ -169,16 +175,22 @@ extern "C" int mvd_warp_im2col_f32(const float* src, const float* Mat, int BN, i
   return MVD_OK;
 }
 
-extern "C" int mvd_upsample_im2col_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, float* A,
-                                       void* stream) {
+extern "C" int mvd_upsample_im2col_rows_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, int row0,
+                                            int nrows, float* A, void* stream) {
   if (!src || !A) return MVD_ERR_NULL_POINTER;
   if (BN <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0 || BN > 65535) return MVD_ERR_BAD_SHAPE;
+  if (row0 < 0 || nrows <= 0 || row0 + nrows > Ho) return MVD_ERR_BAD_SHAPE;
   if (C % 4 != 0) return MVD_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(A)) & 15u) return MVD_ERR_MISALIGNED;
   // ATen area_pixel_compute_scale<float>(in, out, align_corners=false, scale=nullopt): (float)in / out
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  dim3 grid((unsigned)ceil_div64((int64_t)(Ho + 2) * (Wo + 2), kImPix), (unsigned)BN);
-  upsample_im2col_kernel<<<grid, kImThreads, 0, (cudaStream_t)stream>>>(src, C, Hi, Wi, Ho, Wo, sh, sw, A);
+  dim3 grid((unsigned)ceil_div64((int64_t)(nrows + 2) * (Wo + 2), kImPix), (unsigned)BN);
+  upsample_im2col_kernel<<<grid, kImThreads, 0, (cudaStream_t)stream>>>(src, C, Hi, Wi, Ho, Wo, sh, sw, row0, nrows, A);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
+}
+
+extern "C" int mvd_upsample_im2col_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, float* A,
+                                       void* stream) {
+  return mvd_upsample_im2col_rows_f32(src, BN, C, Hi, Wi, Ho, Wo, 0, Ho, A, stream);
 }

@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(kWtThreads, 2)
     }
   }
   __syncthreads();
-  const int xmin = s_box[0], ymin = s_box[1];
+  // TMA fetches 16-byte granules: the innermost (x) start coordinate must be a multiple of 4 floats, otherwise the copy
+  // faults as an illegal instruction (seen on B200). Round down (two's complement: also right for -1 -> -4).
+  const int xmin = s_box[0] & ~3, ymin = s_box[1];
   const bool empty = s_box[2] < xmin;  // no pixel of the tile sees the source image
   const int bbw = empty ? 1 : s_box[2] - xmin + 1, bbh = empty ? 1 : s_box[3] - ymin + 1;
   const int bw = bbw <= 16 ? 16 : (bbw <= 32 ? 32 : 64);

@@ -354,17 +354,20 @@ def warp_im2col(src, M, dsize, stride=2):
     return A, (Ho2, Wo2)
 
 
-def upsample_im2col(x_cl, dsize):
+def upsample_im2col(x_cl, dsize, rows=None):
     """x_cl [BN,Hi,Wi,C] channels-last fp32 CUDA -> im2col matrix [BN*Ho*Wo, 9*C] of a 3x3 / stride-1 / pad-1 convolution
-    over its bilinear upsample (align_corners=False) to dsize."""
+    over its bilinear upsample (align_corners=False) to dsize. rows=(row0, nrows): only that band of output rows
+    ([BN*nrows*Wo, 9*C]; the view-sharded tail)."""
     BN, Hi, Wi, C = x_cl.shape
     Ho, Wo = int(dsize[0]), int(dsize[1])
     if not (x_cl.is_cuda and x_cl.is_contiguous() and x_cl.dtype == torch.float32 and C % 4 == 0):
         raise RuntimeError("upsample_im2col: contiguous fp32 CUDA [BN,Hi,Wi,C] with C % 4 == 0 required")
-    A = torch.empty((BN * Ho * Wo, 9 * C), dtype=x_cl.dtype, device=x_cl.device)
+    row0, nrows = (0, Ho) if rows is None else (int(rows[0]), int(rows[1]))
+    A = torch.empty((BN * nrows * Wo, 9 * C), dtype=x_cl.dtype, device=x_cl.device)
     with _on_device(x_cl):
-        rc = _C.lib.mvd_upsample_im2col_f32(x_cl.data_ptr(), BN, C, Hi, Wi, Ho, Wo, A.data_ptr(), _stream(x_cl))
-    _C.check(rc, "mvd_upsample_im2col_f32")
+        rc = _C.lib.mvd_upsample_im2col_rows_f32(x_cl.data_ptr(), BN, C, Hi, Wi, Ho, Wo, row0, nrows, A.data_ptr(),
+                                                 _stream(x_cl))
+    _C.check(rc, "mvd_upsample_im2col_rows_f32")
     return A
 
 
@@ -397,7 +400,7 @@ def linear_available():
     return int(_C.lib.mvd_linear_available())
 
 
-def linear(x, weight, bias=None, relu=False, mode=None):
+def linear(x, weight, bias=None, relu=False, mode=None, out=None):
     """act(x @ weight.T + bias) for x [rows, K], weight [N, K] (nn.Linear layout), fp32 CUDA, through mvd_linear_f32.
     mode "bf16x9": fp32 emulated on the tensor cores (cuBLASLt 12.9 CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32-level
     accuracy); "fp32": the same library's native fp32; "torch": torch.mm + our bias kernel (explicit opt-in with
@@ -416,7 +419,10 @@ def linear(x, weight, bias=None, relu=False, mode=None):
         ws = _gemm_ws.get(ws_key)
         if ws is None:
             ws = _gemm_ws[ws_key] = torch.empty(64 << 20, dtype=torch.uint8, device=x.device)
-        out = torch.empty((rows, N), dtype=x.dtype, device=x.device)
+        if out is None:
+            out = torch.empty((rows, N), dtype=x.dtype, device=x.device)
+        elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (rows, N)):
+            raise RuntimeError("linear: out must be a contiguous fp32 CUDA tensor [rows, N]")
         with _on_device(x):
             rc = _C.lib.mvd_linear_f32(x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
                                        rows, K, N, 1 if relu else 0, 1 if mode == "bf16x9" else 0, out.data_ptr(),
@@ -429,12 +435,12 @@ def linear(x, weight, bias=None, relu=False, mode=None):
                 f"N={N}, mode={mode}). Set MVDETR_B200_GEMM=torch to run the dense layers through torch.mm instead "
                 "(about 1.5x slower frames); it is never selected silently.")
         _C.check(rc, "mvd_linear_f32")
-    out = torch.mm(x, weight.t())
+    res = torch.mm(x, weight.t(), out=out) if out is not None else torch.mm(x, weight.t())
     if bias is not None and N % 4 == 0:
-        return bias_act_(out, bias, relu=relu)
+        return bias_act_(res, bias, relu=relu)
     if bias is not None:
-        out = out + bias
-    return torch.relu_(out) if relu else out
+        res.add_(bias)
+    return torch.relu_(res) if relu else res
 
 
 def gemm_mode_text():

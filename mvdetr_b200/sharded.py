@@ -12,7 +12,12 @@ contiguous view range [v0, v1):
         value   = ALL-GATHER(value_r)   <-- the one exchange step per layer (5.5 MB / view at Wildtrack size)
         src_r   = layer(src_r, queries of the local views sampling the full `value`)
     memory = ALL-GATHER(src_r)                            (for the merge conv over all views)
-    rank-replicated merge_linear + upsample (identical on every rank; rank 0's copy is the result)
+    tail, sharded by ROWS of the ground grid: every rank runs the (cheap) 1x1 merge over all cells, then upsample +
+    3x3 conv for its own band of output rows only (the band's halo is computed, not exchanged), and one ALL-GATHER of the
+    [rows, C] bands puts the fused feature on every rank (rank 0's copy is the one the caller reads)
+
+Inside each layer the value all-gather runs on the compute stream while the sampling-offset / attention-logit GEMMs of
+the local queries run on a side stream (fork/join with events; both are captured into the same CUDA graph).
 
 The first all-gather is the north star's "all-gather of warped world-grid features before the transformer" (the
 warped features, after the per-view conv and the per-token value projection, both of which commute with the gather).
@@ -78,6 +83,8 @@ class ShardedFusion:
         self.part = ViewPartition(fusion.num_cam, world)
         self.v0, self.v1 = self.part.lo(rank), self.part.hi(rank)
         self._bufs = {}
+        self._side = None       # side stream for the GEMMs that overlap the value all-gather
+        self.shard_tail = True  # False: every rank computes the whole tail (round-1 behaviour, A/B switch)
 
     def _buf(self, key, shape, like):
         b = self._bufs.get(key)
@@ -118,18 +125,38 @@ class ShardedFusion:
                ).view(S, C)[q0:q0 + nq]
         gbuf = self._buf(("gather", slot), (part.world, part.per_rank * hw, C), src_local)
         src = src_local
+        cur = torch.cuda.current_stream(dev) if src_local.is_cuda else None
+        if cur is not None and self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
         for layer in wf.encoder.layers:
             attn = layer.self_attn
             M, L, P = attn.n_heads, attn.n_levels, attn.n_points
             mine = gbuf[rank][:nq]
+            offsets = logits = None
+            if nq and cur is not None:
+                # fork: the two query GEMMs only need local rows; they overlap the value projection + all-gather
+                fork, join = torch.cuda.Event(), torch.cuda.Event()
+                fork.record(cur)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(fork)
+                    query = src + pos
+                    # bias-free GEMMs; the biases are applied inside our kernels (world_feat.MSDeformAttn.forward)
+                    offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
+                    logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
+                    join.record(self._side)
             if nq:
-                torch.addmm(attn.value_proj.bias, src, attn.value_proj.weight.t(), out=mine)  # local rows in place
+                ops.linear(src, attn.value_proj.weight, attn.value_proj.bias, out=mine)  # local rows, in the gather buffer
             value = gather_rows(mine, part, hw, rank, out=gbuf, group=self.group)
             if nq:
-                query = src + pos
-                # bias-free GEMMs; the biases are applied inside our kernels (see world_feat.MSDeformAttn.forward)
-                offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
-                logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
+                if cur is not None:
+                    # join. The side-stream tensors are consumed on this stream; their blocks return to the side stream's
+                    # pool and are only reused by the next layer's side-stream work, which starts after a fork event
+                    # recorded behind the consumer -- no record_stream needed (and none inside graph capture)
+                    cur.wait_event(join)
+                else:
+                    query = src + pos
+                    offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
+                    logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
                 out = ops.msda_fused_forward(value.view(1, S, M, C // M), geo.shapes, geo.start, offsets, logits,
                                              table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm,
                                              off_bias=attn.sampling_offsets.bias, logit_bias=attn.attention_weights.bias)
@@ -143,9 +170,30 @@ class ShardedFusion:
         memory = gather_rows(src, part, hw, rank, out=gbuf, group=self.group)
         if self.fusion.gemm_path and wf.fast_path_ok(memory):
             mem_cm = memory.view(N, hw, C).permute(1, 0, 2).reshape(hw, N * C)  # view-major -> cell-major rows
+            if self.shard_tail and part.world > 1:
+                return self.sharded_tail(mem_cm, Hd, Wd, slot)
             return wf.tail_from_cell_major(mem_cm, Hd, Wd)
         merged = wf.merge_linear(memory.view(1, N, Hd, Wd, C).permute(0, 1, 4, 2, 3).reshape(1, N * C, Hd, Wd))
         return wf.upsample(merged)
+
+    def sharded_tail(self, mem_cm, Hd, Wd, slot):
+        """merge 1x1 conv over all cells on every rank (one small GEMM), then upsample + 3x3 conv for this rank's band
+        of ground-plane rows, all-gather of the bands, NHWC -> NCHW. Same arithmetic per output element as
+        DeformTransWorldFeat.tail_from_cell_major (row partitions of the same GEMM)."""
+        wf, world, rank = self.wf, self.world, self.rank
+        _, Wm, Wu = wf.gemm_weights()
+        C = wf.hidden_dim
+        Hg, Wg = wf.Rworld_shape
+        band = -(-Hg // world)  # ceil: rows per rank; trailing ranks may own fewer or none
+        r0, r1 = min(Hg, rank * band), min(Hg, (rank + 1) * band)
+        merged = ops.linear(mem_cm.contiguous(), Wm, wf.merge_linear[0].bias, relu=True)   # [cells, C] = NHWC map
+        obuf = self._buf(("tail", slot), (world, band * Wg, C), merged)
+        if r1 > r0:
+            A = ops.upsample_im2col(merged.view(1, Hd, Wd, C), (Hg, Wg), rows=(r0, r1 - r0))
+            ops.linear(A, Wu, wf.upsample[1].bias, relu=True, out=obuf[rank][:(r1 - r0) * Wg])
+        dist.all_gather_into_tensor(obuf.view(-1), obuf[rank].reshape(-1), group=self.group)
+        out_cl = obuf.view(world * band * Wg, C)[:Hg * Wg]   # bands are contiguous row ranges: valid rows form a prefix
+        return ops.transpose_last2(out_cl.view(1, Hg * Wg, C)).view(1, C, Hg, Wg)
 
     def fuse(self, feat_local, proj_local, slot=0):
         src, Hd, Wd = self.tokens(feat_local, proj_local)

@@ -15,6 +15,7 @@ __global__ void probe(const int* __restrict__ offs, long long* cyc, float* sink,
   int o = offs[threadIdx.x & 31];  // byte offset for this lane
   float acc = 0.f;
   const unsigned base = (unsigned)__cvta_generic_to_shared(sm);
+  __syncthreads();
   const long long t0 = clock64();
 #pragma unroll 8
   for (int it = 0; it < kIters; ++it) {
@@ -34,6 +35,7 @@ __global__ void probe(const int* __restrict__ offs, long long* cyc, float* sink,
     }
     o ^= (it & 1) ? 2048 : 4096;  // same pattern, different base
   }
+  __syncthreads();  // the whole block: warp 0 alone would only time its own (prioritised) instruction stream
   const long long t1 = clock64();
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
   sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;

@@ -17,12 +17,13 @@ def main():
     device = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    ds, fusion = bench.build_fusion(device)
+    wl = bench.WORKLOADS["wildtrack"]
+    ds, fusion = bench.build_fusion(device, wl)
     wf = fusion.world_feat
     N, (Hg, Wg) = ds.num_cam, ds.Rworld_shape
     Hd, Wd = Hg // 2, Wg // 2
     Lq = S = N * Hd * Wd
-    H, P, C = bench.HEADS, bench.POINTS, bench.HIDDEN
+    H, P, C = wl["heads"], wl["points"], wl["hidden"]
     D = C // H
     g = torch.Generator(device="cpu").manual_seed(1)
     feat = torch.randn(N, C, *ds.Rimg_shape, generator=g).to(device)

@@ -9,7 +9,7 @@ import torch
 from oracle import preprocess_ref as pr
 
 CASES = ("down_1p5", "down_odd", "down_3x", "up", "same")
-TOL = 2e-6  # fp32 rounding of the normalised values (|x| <= 2.7) through two weighted sums
+TOL = 5e-6  # fp32 rounding of the normalised values (|x| <= 2.7, ulp 2.4e-7) through two weighted sums
 
 
 @pytest.mark.parametrize("name", CASES)
