@@ -316,6 +316,20 @@ MVD_API int mvd_linear_f32(const float* x, const float* W, const float* bias, in
                    int precision, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The same Linear layer as OUR kernel on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, accumulators in tensor
+ * memory, operands staged by TMA): out[rows, N] = act(x[rows, K] @ W[N, K]^T + bias[N]) with fp32-level accuracy through a
+ * 3xTF32 split -- x = x_hi + x_lo is split inside the kernel, the weight once by mvd_tf32_split_f32 (hi = RN_tf32(w),
+ * lo = w - hi), out = x_hi w_hi + x_hi w_lo + x_lo w_hi accumulated in fp32 (max error vs fp64 below a native fp32 GEMM).
+ * One launch per layer: no operand scan, no separate bias pass, no workspace.
+ *   replaces the nn.Linear calls of  ref: mvd/models/ops/modules/ms_deform_attn.py:96,100-101,116,
+ *                                         mvd/models/deformable_transformer.py:82
+ *   K % 4 == 0, N % 4 == 0, all pointers 16-byte aligned; bias nullable; relu != 0 applies ReLU.
+ * ------------------------------------------------------------------------------------------ */
+MVD_API int mvd_tf32_split_f32(const float* w, int64_t n, float* hi, float* lo, void* stream);
+MVD_API int mvd_linear_tf32x3_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias,
+                          int64_t rows, int K, int N, int relu, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (used for end-to-end timing and by non-PyTorch callers):
  * same arguments, but every pointer is HOST memory (pinned or pageable). They allocate device
  * scratch, copy in, run the kernel above, copy the result back and synchronise `stream` before

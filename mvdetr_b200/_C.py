@@ -40,6 +40,8 @@ SIGNATURES = {
     "mvd_distance_nms_f32": [_p, _p, _p, _p, _i, _i, ctypes.c_float, _i, _p, ctypes.c_size_t, _p, _p, _p, _p, _p, _p],
     "mvd_linear_available": [],
     "mvd_linear_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p],
+    "mvd_tf32_split_f32": [_p, ctypes.c_int64, _p, _p, _p],
+    "mvd_linear_tf32x3_f32": [_p, _p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_bias_act_f32": [_p, _p, ctypes.c_int64, _i, _i, _p],
     "mvd_warp_fwd_f32": [_p, _p] + [_i] * 6 + [_p, _i, _p],
     "mvd_warp_tma_f32": [_p, _p] + [_i] * 6 + [_p, _i, _i, _p],

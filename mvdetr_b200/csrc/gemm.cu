@@ -112,60 +112,9 @@ bool load_lt() {
   return false;
 }
 
-// Optional on-device selection among the heuristic's candidates (MVD_GEMM_AUTOTUNE=1; EXPERIMENTAL, off by default):
-// each valid candidate runs once untimed and three times between CUDA events on the caller's stream, with the
-// caller's real operands (the output is overwritten again by the real call). Skipped while the stream is capturing.
-struct TuneArgs {
-  const float* W;
-  const float* x;
-  float* out;
-  void* workspace;
-  size_t workspace_bytes;
-  cudaStream_t stream;
-};
-
-bool autotune_enabled() {
-  const char* e = getenv("MVD_GEMM_AUTOTUNE");
-  return e && e[0] == '1';
-}
-
-int pick_fastest(const Plan& p, const cublasLtMatmulHeuristicResult_t* res, int found, size_t ws_avail, const TuneArgs& t) {
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(t.stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return -1;
-  cudaEvent_t e0, e1;
-  if (cudaEventCreate(&e0) != cudaSuccess) return -1;
-  if (cudaEventCreate(&e1) != cudaSuccess) {
-    cudaEventDestroy(e0);
-    return -1;
-  }
-  const float alpha = 1.f, beta = 0.f;
-  int best = -1;
-  float best_ms = 0.f;
-  for (int i = 0; i < found; ++i) {
-    if (res[i].state != CUBLAS_STATUS_SUCCESS || res[i].workspaceSize > ws_avail) continue;
-    bool ok = true;
-    for (int rep = 0; rep < 4 && ok; ++rep) {
-      if (rep == 1) cudaEventRecord(e0, t.stream);
-      ok = g_lt.Matmul(g_lt.handle, p.desc, &alpha, t.W, p.a, t.x, p.b, &beta, t.out, p.c, t.out, p.c, &res[i].algo,
-                       t.workspace, t.workspace_bytes, t.stream) == CUBLAS_STATUS_SUCCESS;
-    }
-    cudaEventRecord(e1, t.stream);
-    float ms = 0.f;
-    if (!ok || cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) continue;
-    if (best < 0 || ms < best_ms) {
-      best = i;
-      best_ms = ms;
-    }
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  return best;
-}
-
 // Lock held. Row-major out[rows, N] = x[rows, K] @ W[N, K]^T is, in cuBLAS' column-major terms,
 // C'(N x rows, ld N) = op_T(A = W as K x N, ld K) * (B = x as K x rows, ld K).
-int make_plan(int64_t rows, int K, int N, int epi, int precision, const float* bias, size_t ws_avail, Plan* out,
-              const TuneArgs* tune = nullptr) {
+int make_plan(int64_t rows, int K, int N, int epi, int precision, const float* bias, size_t ws_avail, Plan* out) {
   Plan p;
   const cublasComputeType_t ct = precision ? CUBLAS_COMPUTE_32F_EMULATED_16BFX9 : CUBLAS_COMPUTE_32F;
   if (g_lt.DescCreate(&p.desc, ct, CUDA_R_32F) != CUBLAS_STATUS_SUCCESS) return MVD_ERR_UNSUPPORTED;
@@ -185,16 +134,14 @@ int make_plan(int64_t rows, int K, int N, int epi, int precision, const float* b
   okc = okc && g_lt.PrefCreate(&pref) == CUBLAS_STATUS_SUCCESS;
   int found = 0;
   cublasLtMatmulHeuristicResult_t res[16];
-  const bool tuning = tune != nullptr && autotune_enabled();
   if (okc) {
     g_lt.PrefSet(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &ws_avail, sizeof(ws_avail));
-    if (g_lt.Heuristic(g_lt.handle, p.desc, p.a, p.b, p.c, p.c, pref, tuning ? 16 : 4, res, &found) !=
+    if (g_lt.Heuristic(g_lt.handle, p.desc, p.a, p.b, p.c, p.c, pref, 4, res, &found) !=
         CUBLAS_STATUS_SUCCESS)
       found = 0;
   }
   if (pref) g_lt.PrefDestroy(pref);
   int pick = -1;
-  if (tuning && found > 1) pick = pick_fastest(p, res, found, ws_avail, *tune);
   for (int i = 0; i < found && pick < 0; ++i)
     if (res[i].state == CUBLAS_STATUS_SUCCESS && res[i].workspaceSize <= ws_avail) pick = i;
   if (pick < 0) {
@@ -240,8 +187,7 @@ extern "C" int mvd_linear_f32(const float* x, const float* W, const float* bias,
   auto it = g_plans.find(key);
   if (it == g_plans.end()) {
     Plan p;
-    const TuneArgs tune{W, x, out, workspace, workspace ? workspace_bytes : 0, (cudaStream_t)stream};
-    const int e = make_plan(rows, K, N, epi, precision, bias, workspace ? workspace_bytes : 0, &p, &tune);
+    const int e = make_plan(rows, K, N, epi, precision, bias, workspace ? workspace_bytes : 0, &p);
     if (e != MVD_OK && e != MVD_ERR_UNSUPPORTED) return e;
     it = g_plans.emplace(key, p).first;  // p.valid == false records "no algorithm": the query is not repeated
   }

@@ -250,6 +250,228 @@ __global__ void __launch_bounds__(kWtThreads, 2)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Channels-last / im2col destinations, second formulation (r02c profile of the kernel above: 117 us, latency-bound, 3.7 k
+// instructions per warp -- a scalar shared load per tap AND per channel plus a [32][257] output transposition).
+// A ground-plane tile reads a SMALL patch of the camera image (median 36 source pixels for 256 destination pixels), so
+// the relayout is done on the patch, not on the output:
+//   1. TMA stages the patch as [channel][row][x] (NCHW boxes, as above);
+//   2. the block transposes the patch to pixel-major [patch pixel][CH + 4] (a few thousand elements);
+//   3. every destination pixel then reads each tap as ONE contiguous channel vector: lanes = channel quads, 128-bit
+//      shared loads, bank-conflict free, and the result leaves as 128-bit stores of consecutive channels
+//      (512 contiguous bytes per pixel at CH = 128) -- no output transposition, ~4x fewer instructions.
+// CH (channels per pass) is the largest of {128, 64, 32, 16, 8} whose staged patch fits; tiles whose patch does not fit
+// even at CH = 8 (strong minification) gather straight from global memory with the same lane mapping.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWcRaw = 8192;    // floats per raw (TMA) stage, two stages
+constexpr int kWcTr = 8704;     // floats of the transposed patch
+constexpr int kWcBoxes = 6;     // TMA box widths {8, 16, 24, 32, 48, 64} floats x 4 rows x 8 channels
+__device__ __constant__ int kWcBw[kWcBoxes] = {8, 16, 24, 32, 48, 64};
+constexpr int kWcBoxCh = 8;     // channels per TMA box (so that every CH is a whole number of boxes)
+
+struct WcMaps {
+  CUtensorMap m[kWcBoxes];
+};
+
+template <int MODE, int S>
+__global__ void __launch_bounds__(kWtThreads, 2) warp_tma_cl_kernel(const __grid_constant__ WcMaps maps, const WtParams prm) {
+  constexpr int TH = 16, TW = 16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* raw = reinterpret_cast<float*>(smem_raw);  // 2 x kWcRaw
+  float* tr = raw + 2 * kWcRaw;                     // kWcTr
+  int* s_off = reinterpret_cast<int*>(tr + kWcTr);  // [256] element offset of the north-west tap in `tr` (pixel index)
+  float* s_w = reinterpret_cast<float*>(s_off + kWtThreads);  // [4][256] tap weights (0 for pixels without a valid tap)
+  __shared__ float sT[9];
+  __shared__ int s_box[4];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+
+  const int C = prm.C, Hi = prm.Hi, Wi = prm.Wi, Ho = prm.Ho, Wo = prm.Wo;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int PAD = (MODE == WT_IM2COL) ? 1 : 0;
+  const int ty0 = (blockIdx.x / prm.tiles_x) * TH - PAD, tx0 = (blockIdx.x % prm.tiles_x) * TW - PAD;
+  const uint32_t bar0 = smem_u32(&s_bar[0]);
+
+  if (tid == 0) {
+    normalized_inverse(prm.Mat + 9 * n, Hi, Wi, Ho, Wo, sT);
+    s_box[0] = s_box[1] = 0x7fffffff;
+    s_box[2] = s_box[3] = -0x7fffffff;
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int v = ty0 + tid / TW, u = tx0 + tid % TW;
+  const bool real = v >= 0 && v < Ho && u >= 0 && u < Wo;
+  const Taps t = make_taps(sT, real ? u : 0, real ? v : 0, Hi, Wi, Ho, Wo);
+  const bool valid = real && (t.m_nw || t.m_ne || t.m_sw || t.m_se);
+  {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int big = 0x7fffffff;
+    int xl = valid ? t.x0 : big, yl = valid ? t.y0 : big, xh = valid ? t.x0 + 1 : -big, yh = valid ? t.y0 + 1 : -big;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      xl = min(xl, __shfl_xor_sync(FULL, xl, d));
+      yl = min(yl, __shfl_xor_sync(FULL, yl, d));
+      xh = max(xh, __shfl_xor_sync(FULL, xh, d));
+      yh = max(yh, __shfl_xor_sync(FULL, yh, d));
+    }
+    if (lane == 0 && xl != big) {
+      atomicMin(&s_box[0], xl);
+      atomicMin(&s_box[1], yl);
+      atomicMax(&s_box[2], xh);
+      atomicMax(&s_box[3], yh);
+    }
+  }
+  __syncthreads();
+  // patch = [xmin, xmax] x [ymin, ymax]; the TMA start coordinate must be a multiple of 4 floats (16 bytes)
+  const int xmin = s_box[0] & ~3, ymin = s_box[1];
+  const bool empty = s_box[2] < xmin;
+  const int bbw = empty ? 1 : s_box[2] - xmin + 1, bbh = empty ? 1 : s_box[3] - ymin + 1;
+  int bsel = 0;
+  while (bsel < kWcBoxes - 1 && kWcBw[bsel] < bbw) ++bsel;
+  const int bw = kWcBw[bsel];
+  const int hg = (bbh + kWtRows - 1) / kWtRows;
+  // largest channel pass whose raw boxes and transposed patch both fit
+  int CH = 0;
+  if (!empty && bbw <= 64) {
+    for (int c = 128; c >= 8; c >>= 1) {
+      if (c <= C && C % c == 0 && bw * kWtRows * hg * c <= kWcRaw && bbw * bbh * (c + 4) <= kWcTr) {
+        CH = c;
+        break;
+      }
+    }
+  }
+  const bool staged = CH > 0;
+  if (!staged) CH = (C % 128 == 0) ? 128 : 32;  // global-memory path: same lane mapping
+  const int nchunks = C / CH;
+  const int pitch = CH + 4;
+
+  // per-pixel tap records for the gather (one thread = one pixel wrote them; any warp reads them)
+  s_off[tid] = valid ? ((t.y0 - ymin) * bbw + (t.x0 - xmin)) : -1;
+  s_w[tid] = valid ? t.nw : 0.f;
+  s_w[kWtThreads + tid] = valid ? t.ne : 0.f;
+  s_w[2 * kWtThreads + tid] = valid ? t.sw : 0.f;
+  s_w[3 * kWtThreads + tid] = valid ? t.se : 0.f;
+
+  auto issue_chunk = [&](int ch) {  // one thread: channels [ch*CH, (ch+1)*CH) of the patch -> raw stage ch & 1
+    const uint32_t bar = bar0 + 8u * (uint32_t)(ch & 1);
+    const uint32_t st = smem_u32(raw + (size_t)(ch & 1) * kWcRaw);
+    const uint32_t box_bytes = (uint32_t)(bw * kWtRows * kWcBoxCh * 4);
+    const int nb = CH / kWcBoxCh;
+    mbar_expect_tx(bar, (uint32_t)nb * (uint32_t)hg * box_bytes);
+    for (int g = 0; g < hg; ++g)
+      for (int b = 0; b < nb; ++b)  // raw layout: [row group g][channel][4 rows][bw]
+      {  // the tensor map operand is named statically (one case per box width), never a computed address
+        const uint32_t dst = st + (uint32_t)(g * nb + b) * box_bytes;
+        const int cy = ymin + g * kWtRows, cc = ch * CH + b * kWcBoxCh;
+        switch (bsel) {
+          case 0: tma_load_4d(dst, &maps.m[0], bar, xmin, cy, cc, n); break;
+          case 1: tma_load_4d(dst, &maps.m[1], bar, xmin, cy, cc, n); break;
+          case 2: tma_load_4d(dst, &maps.m[2], bar, xmin, cy, cc, n); break;
+          case 3: tma_load_4d(dst, &maps.m[3], bar, xmin, cy, cc, n); break;
+          case 4: tma_load_4d(dst, &maps.m[4], bar, xmin, cy, cc, n); break;
+          default: tma_load_4d(dst, &maps.m[5], bar, xmin, cy, cc, n); break;
+        }
+      }
+  };
+  if (staged && tid == 0) {
+    issue_chunk(0);
+    if (nchunks > 1) issue_chunk(1);
+  }
+  __syncthreads();  // tap records visible
+
+  const int QL = CH / 4;             // lanes per pixel (channel quads)
+  const int PPI = 32 / (QL < 32 ? QL : 32);  // pixels per warp instruction
+  const int q = lane % QL, psub = lane / QL;
+  const int64_t plane = (int64_t)Hi * Wi;
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int c0 = ch * CH;
+    if (staged) {
+      mbar_wait(bar0 + 8u * (uint32_t)(ch & 1), (uint32_t)((ch >> 1) & 1));
+      // ---- transpose the patch: raw [g][c][4][bw] -> tr [y*bbw + x][CH + 4] ----
+      const float* rp = raw + (size_t)(ch & 1) * kWcRaw;
+      const int npx = bbw * bbh;
+      for (int e = tid; e < npx * CH; e += kWtThreads) {
+        const int c = e / npx, px = e - c * npx;  // lanes along the patch pixels: consecutive x read consecutive words
+        const int y = px / bbw, x = px - y * bbw;
+        tr[px * pitch + c] = rp[(((y >> 2) * CH + c) * kWtRows + (y & 3)) * bw + x];
+      }
+      __syncthreads();
+      if (tid == 0 && ch + 2 < nchunks) {  // the raw stage is free again
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_chunk(ch + 2);
+      }
+    }
+    // ---- gather: warp w owns tile pixels [32w, 32w + 32); PPI pixels per instruction, lane = channel quad ----
+    for (int it = 0; it < 32 / PPI; ++it) {
+      const int p = warp * 32 + it * PPI + psub;
+      const int pv = ty0 + p / TW, pu = tx0 + p % TW;
+      const int o = s_off[p];
+      const float wnw = s_w[p], wne = s_w[kWtThreads + p], wsw = s_w[2 * kWtThreads + p], wse = s_w[3 * kWtThreads + p];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o >= 0) {
+        float4 q0, q1, q2, q3;
+        if (staged) {
+          const float* b = tr + o * pitch + 4 * q;
+          q0 = *reinterpret_cast<const float4*>(b);
+          q1 = *reinterpret_cast<const float4*>(b + pitch);
+          q2 = *reinterpret_cast<const float4*>(b + bbw * pitch);
+          q3 = *reinterpret_cast<const float4*>(b + (bbw + 1) * pitch);
+        } else {  // patch too large to stage: masked global loads of the 4 channels of this lane
+          const int y0 = o / bbw + ymin, x0 = o - (o / bbw) * bbw + xmin;
+          const bool top = y0 >= 0, bot = y0 + 1 <= Hi - 1, lef = x0 >= 0, rig = x0 + 1 <= Wi - 1;
+          const float* g = prm.src + ((int64_t)n * C + c0 + 4 * q) * plane + (int64_t)y0 * Wi + x0;
+          float a0[4], a1[4], a2[4], a3[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float* gk = g + (int64_t)k * plane;
+            a0[k] = (top && lef) ? __ldg(gk) : 0.f;
+            a1[k] = (top && rig) ? __ldg(gk + 1) : 0.f;
+            a2[k] = (bot && lef) ? __ldg(gk + Wi) : 0.f;
+            a3[k] = (bot && rig) ? __ldg(gk + Wi + 1) : 0.f;
+          }
+          q0 = make_float4(a0[0], a0[1], a0[2], a0[3]);
+          q1 = make_float4(a1[0], a1[1], a1[2], a1[3]);
+          q2 = make_float4(a2[0], a2[1], a2[2], a2[3]);
+          q3 = make_float4(a3[0], a3[1], a3[2], a3[3]);
+        }
+        acc.x = fmaf(q3.x, wse, fmaf(q2.x, wsw, fmaf(q1.x, wne, q0.x * wnw)));
+        acc.y = fmaf(q3.y, wse, fmaf(q2.y, wsw, fmaf(q1.y, wne, q0.y * wnw)));
+        acc.z = fmaf(q3.z, wse, fmaf(q2.z, wsw, fmaf(q1.z, wne, q0.z * wnw)));
+        acc.w = fmaf(q3.w, wse, fmaf(q2.w, wsw, fmaf(q1.w, wne, q0.w * wnw)));
+      }
+      const int c = c0 + 4 * q;
+      if (MODE == WT_NHWC) {
+        if (pv < Ho && pu < Wo) st_stream4(prm.dst + (((int64_t)n * Ho + pv) * Wo + pu) * C + c, acc);
+      } else {
+        const int vp = pv + 1, up = pu + 1;  // padded coordinates, >= 0
+        if (vp <= Ho + 1 && up <= Wo + 1) {
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int a = vp - ky;
+            if (a < 0 || (a % S) != 0) continue;
+            const int oy = a / S;
+            if (oy >= prm.Ho2) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int b = up - kx;
+              if (b < 0 || (b % S) != 0) continue;
+              const int ox = b / S;
+              if (ox >= prm.Wo2) continue;
+              st_stream4(prm.dst + ((((int64_t)n * prm.Ho2 + oy) * prm.Wo2 + ox) * 9 + ky * 3 + kx) * C + c, acc);
+            }
+          }
+        }
+      }
+    }
+    if (staged && ch + 1 < nchunks) __syncthreads();  // everyone is done with `tr` before the next pass overwrites it
+  }
+}
+
 int encode_src_map(CUtensorMap* map, const float* src, int BN, int C, int Hi, int Wi, int bw) {
   const cuuint64_t u = 1;
   const cuuint64_t gdim[4] = {u * Wi, u * Hi, u * C, u * BN};
@@ -271,6 +493,28 @@ int launch_wt(const CUtensorMap* maps, WtParams prm, int BN, int dom_h, int dom_
   return MVD_OK;
 }
 
+template <int MODE, int S>
+int launch_wc(const float* src, int BN, int C, int Hi, int Wi, WtParams prm, int dom_h, int dom_w, cudaStream_t st) {
+  WcMaps maps;
+  const int bws[kWcBoxes] = {8, 16, 24, 32, 48, 64};
+  for (int i = 0; i < kWcBoxes; ++i) {
+    const cuuint64_t u = 1;
+    const cuuint64_t gdim[4] = {u * Wi, u * Hi, u * C, u * BN};
+    const cuuint64_t gstr[3] = {u * Wi * 4, u * Hi * Wi * 4, u * C * Hi * Wi * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)bws[i], (cuuint32_t)kWtRows, (cuuint32_t)kWcBoxCh, 1u};
+    if (int e = encode(&maps.m[i], src, 4, gdim, gstr, box)) return e;
+  }
+  auto kern = warp_tma_cl_kernel<MODE, S>;
+  const size_t smem = (size_t)(2 * kWcRaw + kWcTr) * 4 + (size_t)kWtThreads * 5 * 4;
+  MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prm.tiles_x = (dom_w + 15) / 16;
+  const int tiles_y = (dom_h + 15) / 16;
+  dim3 grid((unsigned)(prm.tiles_x * tiles_y), (unsigned)BN);
+  kern<<<grid, kWtThreads, smem, st>>>(maps, prm);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
+
 }  // namespace
 }  // namespace mvd
 
@@ -288,10 +532,6 @@ extern "C" int mvd_warp_tma_f32(const float* src, const float* Mat, int BN, int 
   if (C % kWtCC != 0 || Wi % 4 != 0) return MVD_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) return MVD_ERR_MISALIGNED;
   cudaStream_t st = (cudaStream_t)stream;
-  alignas(64) CUtensorMap maps[3];
-  const int bws[3] = {16, 32, 64};
-  for (int i = 0; i < 3; ++i)
-    if (int e = encode_src_map(&maps[i], src, BN, C, Hi, Wi, bws[i])) return e;
   WtParams prm;
   prm.src = src;
   prm.Mat = Mat;
@@ -303,11 +543,17 @@ extern "C" int mvd_warp_tma_f32(const float* src, const float* Mat, int BN, int 
   prm.Wo = Wo;
   prm.tiles_x = 0;
   prm.Ho2 = prm.Wo2 = 0;
-  if (mode == 0) return launch_wt<WT_NCHW, 8, 32, 1>(maps, prm, BN, Ho, Wo, st);
-  if (mode == 1) return launch_wt<WT_NHWC, 16, 16, 1>(maps, prm, BN, Ho, Wo, st);
+  if (mode == 0) {
+    alignas(64) CUtensorMap maps[3];
+    const int bws[3] = {16, 32, 64};
+    for (int i = 0; i < 3; ++i)
+      if (int e = encode_src_map(&maps[i], src, BN, C, Hi, Wi, bws[i])) return e;
+    return launch_wt<WT_NCHW, 8, 32, 1>(maps, prm, BN, Ho, Wo, st);
+  }
+  if (mode == 1) return launch_wc<WT_NHWC, 1>(src, BN, C, Hi, Wi, prm, Ho, Wo, st);
   prm.Ho2 = (Ho + 2 - 3) / stride + 1;
   prm.Wo2 = (Wo + 2 - 3) / stride + 1;
   if ((int64_t)BN * prm.Ho2 * prm.Wo2 * 9 * C > 0x7fffffffffLL) return MVD_ERR_BAD_SHAPE;
-  if (stride == 2) return launch_wt<WT_IM2COL, 16, 16, 2>(maps, prm, BN, Ho + 2, Wo + 2, st);
-  return launch_wt<WT_IM2COL, 16, 16, 1>(maps, prm, BN, Ho + 2, Wo + 2, st);
+  if (stride == 2) return launch_wc<WT_IM2COL, 2>(src, BN, C, Hi, Wi, prm, Ho + 2, Wo + 2, st);
+  return launch_wc<WT_IM2COL, 1>(src, BN, C, Hi, Wi, prm, Ho + 2, Wo + 2, st);
 }

@@ -391,8 +391,26 @@ def _as_nhwc(x):
     return transpose_last2(x.view(N, C, H * W)).view(N, H, W, C), True
 
 
-_GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x9")  # "bf16x9" | "fp32" (cuBLASLt 12.9 native) | "torch"
+# "tf32x3": OUR tcgen05 kernel (3xTF32 split, fp32-level accuracy) | "bf16x9" / "fp32": cuBLASLt 12.9 | "torch"
+_GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x9")
 _gemm_ws = {}
+_tf32_split_cache = {}
+
+
+def _tf32_split(weight):
+    """(hi, lo) fp32 tensors with hi = RN_tf32(weight), lo = weight - hi; computed on the device once per weight
+    version (a few hundred KB each) and cached."""
+    key = (weight.device, weight.data_ptr(), tuple(weight.shape))
+    got = _tf32_split_cache.get(key)
+    if got is None or got[0] != weight._version:
+        hi, lo = torch.empty_like(weight), torch.empty_like(weight)
+        with _on_device(weight):
+            rc = _C.lib.mvd_tf32_split_f32(weight.data_ptr(), weight.numel(), hi.data_ptr(), lo.data_ptr(), _stream(weight))
+        _C.check(rc, "mvd_tf32_split_f32")
+        if len(_tf32_split_cache) > 256:
+            _tf32_split_cache.clear()
+        got = _tf32_split_cache[key] = (weight._version, hi, lo)
+    return got[1], got[2]
 
 
 def linear_available():
@@ -410,6 +428,21 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
     rows, K = x.shape
     N = weight.shape[0]
     x = x.contiguous()
+    if mode == "tf32x3":
+        for name, t in (("x", x), ("weight", weight), ("bias", bias)):
+            if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise RuntimeError(f"linear: {name} must be a contiguous fp32 CUDA tensor")
+        if out is None:
+            out = torch.empty((rows, N), dtype=x.dtype, device=x.device)
+        elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (rows, N)):
+            raise RuntimeError("linear: out must be a contiguous fp32 CUDA tensor [rows, N]")
+        w_hi, w_lo = _tf32_split(weight.detach())
+        with _on_device(x):
+            rc = _C.lib.mvd_linear_tf32x3_f32(x.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
+                                              bias.data_ptr() if bias is not None else None, rows, K, N,
+                                              1 if relu else 0, out.data_ptr(), _stream(x))
+        _C.check(rc, "mvd_linear_tf32x3_f32")
+        return out
     if mode != "torch":
         for name, t in (("x", x), ("weight", weight), ("bias", bias)):
             if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
@@ -448,6 +481,9 @@ def gemm_mode_text():
     lt = linear_available()
     if _GEMM_MODE == "torch":
         return "torch.mm fp32 (cuBLAS SIMT), explicit MVDETR_B200_GEMM=torch"
+    if _GEMM_MODE == "tf32x3":
+        return ("tf32x3: own tcgen05.mma.kind::tf32 kernel (3xTF32 split in-kernel, fp32 accumulate in TMEM, bias/ReLU "
+                "epilogue), fp32-level accuracy")
     if not lt:
         return "UNAVAILABLE: cuBLASLt >= 12.9 not loadable (ops.linear raises)"
     return (f"{_GEMM_MODE} via cuBLASLt {lt} (fp32 in/out; bf16x9 = CUBLAS_COMPUTE_32F_EMULATED_16BFX9, fp32-accurate "

@@ -39,3 +39,27 @@ def test_linear_torch_mode_needs_no_library(cuda):
     x, w, b = _problem(513, 128, 130, 5, cuda)  # N % 4 != 0 -> plain torch epilogue
     got = ops.linear(x, w, b, relu=True, mode="torch")
     assert torch.allclose(got, torch.relu(torch.addmm(b, x, w.t())), atol=1e-6)
+
+
+@pytest.mark.parametrize("rows,K,N", [(75600, 128, 128), (4099, 128, 448), (2048, 128, 224), (3000, 128, 512),
+                                      (3000, 512, 128), (1000, 1152, 128), (77, 896, 128), (130, 36, 20), (1, 4, 4),
+                                      (129, 2304, 256)])
+def test_tf32x3_kernel_is_fp32_accurate(cuda, rows, K, N):
+    """Our tcgen05 kernel (3xTF32 split, accumulators in tensor memory): at least as accurate as the native fp32 GEMM,
+    measured against an fp64 product; bias / ReLU epilogue, row and column tails, K not a multiple of the 32-wide chunk."""
+    x, w, b = _problem(rows, K, N, rows + N + 1, cuda)
+    exact = x.double() @ w.double().t() + b.double()
+    err_torch = (torch.addmm(b, x, w.t()).double() - exact).abs().max().item()
+    tol = max(2 * err_torch, 1e-6 * exact.abs().max().item())
+    got = ops.linear(x, w, b, mode="tf32x3")
+    assert (got.double() - exact).abs().max().item() <= tol
+    relu = ops.linear(x, w, b, relu=True, mode="tf32x3")
+    assert (relu.double() - exact.clamp_min(0)).abs().max().item() <= tol
+    out = torch.full((rows, N), float("nan"), device=cuda)
+    nobias = ops.linear(x, w, None, mode="tf32x3", out=out)
+    assert nobias.data_ptr() == out.data_ptr()
+    assert (nobias.double() - (exact - b.double())).abs().max().item() <= tol
+    # weight updated in place: the cached hi/lo split must follow
+    w.mul_(2.0)
+    again = ops.linear(x, w, None, mode="tf32x3")
+    assert (again.double() - 2 * (exact - b.double())).abs().max().item() <= 2 * tol
