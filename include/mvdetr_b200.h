@@ -326,6 +326,16 @@ MVD_API int mvd_linear_f32(const float* x, const float* W, const float* bias, in
  *   K % 4 == 0, N % 4 == 0, all pointers 16-byte aligned; bias nullable; relu != 0 applies ReLU.
  * ------------------------------------------------------------------------------------------ */
 MVD_API int mvd_tf32_split_f32(const float* w, int64_t n, float* hi, float* lo, void* stream);
+/* Preferred variant: three-term bf16 split (a = a0 + a1 + a2), the six products with i + j <= 2 through
+ * tcgen05.mma.kind::f16 -- bf16 products are exact in the tensor core's adder, so the error is at cuBLASLt BF16x9's level
+ * (below a native fp32 GEMM) with 6 instead of 9 products. Persistent, warp-specialised kernel: TMA producer warp, MMA
+ * warp, 4 splitter warps, 4 epilogue warps; 3-stage operand ring; two accumulators in tensor memory so a tile's
+ * epilogue overlaps the next tile's main loop.
+ *   mvd_bf16_split3_f32: w [n] fp32 -> terms [3][n] bf16 (device, 16-byte aligned), once per weight.
+ *   mvd_linear_bf16x3_f32: x [rows, K] fp32, w_terms [3][N][K] bf16; K % 8 == 0, N % 4 == 0. */
+MVD_API int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void* stream);
+MVD_API int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
+                          int relu, float* out, void* stream);
 MVD_API int mvd_linear_tf32x3_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                           int64_t rows, int K, int N, int relu, float* out, void* stream);
 

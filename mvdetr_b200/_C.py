@@ -42,6 +42,8 @@ SIGNATURES = {
     "mvd_linear_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p],
     "mvd_tf32_split_f32": [_p, ctypes.c_int64, _p, _p, _p],
     "mvd_linear_tf32x3_f32": [_p, _p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
+    "mvd_bf16_split3_f32": [_p, ctypes.c_int64, _p, _p],
+    "mvd_linear_bf16x3_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_bias_act_f32": [_p, _p, ctypes.c_int64, _i, _i, _p],
     "mvd_warp_fwd_f32": [_p, _p] + [_i] * 6 + [_p, _i, _p],
     "mvd_warp_tma_f32": [_p, _p] + [_i] * 6 + [_p, _i, _i, _p],

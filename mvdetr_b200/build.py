@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmvdetr_b200.so")
-SOURCES = ["capi.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_viewgrid.cu", "msda_bwd_viewgrid.cu", "warp.cu", "warp_tma.cu", "layernorm.cu", "gemm.cu", "gemm_tf32.cu", "im2col.cu", "decode.cu", "preprocess.cu"]
+SOURCES = ["capi.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_viewgrid.cu", "msda_bwd_viewgrid.cu", "warp.cu", "warp_tma.cu", "layernorm.cu", "gemm.cu", "gemm_tf32.cu", "gemm_bf16x3.cu", "im2col.cu", "decode.cu", "preprocess.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -1,0 +1,366 @@
+// Dense glue of the path on the 5th-generation tensor cores with fp32-level accuracy, as ONE persistent kernel per layer:
+//   out[rows, N] = act(x[rows, K] @ W[N, K]^T + bias[N])
+//   replaces the six nn.Linear calls per encoder layer  ref: multiview_detector/models/ops/modules/ms_deform_attn.py:96,100-101,116,
+//                                                        multiview_detector/models/deformable_transformer.py:82
+//   and, through the im2col matrices written by warp_tma.cu / im2col.cu, the convolutions of
+//                                                        ref: multiview_detector/models/trans_world_feat.py:74,82-84
+//
+// Why ours: round 1 used cuBLASLt's CUBLAS_COMPUTE_32F_EMULATED_16BFX9 -- 9 bf16 products, a bias pass and a separate
+// Inf/NaN operand-scan kernel per call (profiles/r02c_timeline.txt: GEMM 1.34 ms + scan/patch 0.8 ms of a 3.2 ms frame).
+// The layers are tall-skinny (75 600 x 128 by 128 x {128..512}; ~10 flop/byte): HBM-bound, so the job is to stream x once.
+//
+// Arithmetic: fp32 operands are split into three bf16 terms (a = a0 + a1 + a2, each the bf16 rounding of the remaining
+// residual; 24 mantissa bits covered) and the SIX products with i + j <= 2 are accumulated in fp32 in tensor memory
+// (scripts/emulate_bf16_split.py: the dropped three are below 2^-24 |a||b|; measured error vs fp64 at cuBLASLt BF16x9's
+// level, below a native fp32 GEMM). bf16 products are exact inside the tensor core's adder (16-bit significands), which
+// a 3xTF32 split is not (22-bit products: csrc/gemm_tf32.cu measures 5-10x larger error).
+//
+// Structure (1 CTA per SM, persistent over 128 x 128 output tiles, 320 threads, 3-stage ring, warp-specialised):
+//   warp 0      TMA producer: per 32-wide K chunk the x tile [128 x 32] fp32 (SWIZZLE_128B) and the three pre-split
+//               weight tiles [128 x 32] bf16 (SWIZZLE_64B; rows past `rows` / `N`, columns past K are zero-filled);
+//   warps 2-5   split the x tile into three bf16 tiles in the UMMA K-major SWIZZLE_64B layout (thread = row: conflict-
+//               free 16-byte reads of the 128B-swizzled source and 16-byte writes of the 64B-swizzled destinations);
+//   warp 1      one thread issues 2 k-steps x 6 tcgen05.mma.kind::f16 (M 128, N 128, K 16) per chunk, commits the stage
+//               back to the producer, and after the last chunk commits the accumulator to the epilogue;
+//   warps 6-9   epilogue: tcgen05.ld 32 lanes x 16 columns at a time, + bias, ReLU, 16-byte stores of their own rows,
+//               overlapping the next tile's main loop (two 128-column accumulators in tensor memory).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "vg_common.cuh"
+
+namespace mvd {
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32, kBStages = 3;
+constexpr int kBThreads = 320;
+constexpr int kRawBytes = kBM * kBK * 4;      // 16 KB fp32 x tile
+constexpr int kHalfBytes = kBM * kBK * 2;     // 8 KB bf16 tile (x split or weight term)
+constexpr int kStageBytes = kRawBytes + 6 * kHalfBytes;  // 64 KB
+constexpr int kBSmem = kBStages * kStageBytes + 1024;    // + slack for 1024-byte alignment
+constexpr uint32_t kBTmemCols = 256;          // two 128-column fp32 accumulators
+
+struct GbParams {
+  const float* bias;  // nullable
+  float* out;
+  int rows, K, N, relu;
+  int m_blocks, n_tiles;
+};
+
+__device__ __forceinline__ void tma_load_2d_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major tile of 64-byte rows (SWIZZLE_64B, layout code 4): 8-row groups 512 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+// D fp32 (c_format 1), A and B bf16 (format 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) |
+                                ((uint32_t)(kBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdescBf16), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {  // arrives when every MMA issued so far has retired
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// three-term bf16 split of 8 consecutive floats -> one 16-byte piece per term
+__device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& t0, uint4& t1, uint4& t2) {
+  const float a[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+  float h[8], m[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __bfloat162float(__float2bfloat16_rn(a[i]));
+    const float r1 = a[i] - h[i];  // exact
+    m[i] = __bfloat162float(__float2bfloat16_rn(r1));
+    l[i] = r1 - m[i];              // exact; rounded to bf16 by the pack below
+  }
+  t0 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+  t1 = make_uint4(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]), pack_bf16(m[4], m[5]), pack_bf16(m[6], m[7]));
+  t2 = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+}
+
+__global__ void __launch_bounds__(kBThreads, 1)
+    linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                         const GbParams prm) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) unsigned long long s_bar[3 * kBStages + 4];  // full, conv, empty per stage; tfull[2], tempty[2]
+  __shared__ uint32_t s_tmem;
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bars = smem_u32(&s_bar[0]);
+  auto bar_full = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto bar_conv = [&](int s) { return bars + 8u * (uint32_t)(kBStages + s); };
+  auto bar_empty = [&](int s) { return bars + 8u * (uint32_t)(2 * kBStages + s); };
+  auto bar_tfull = [&](int b) { return bars + 8u * (uint32_t)(3 * kBStages + b); };
+  auto bar_tempty = [&](int b) { return bars + 8u * (uint32_t)(3 * kBStages + 2 + b); };
+
+  if (tid == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_conv(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull(b), 1);
+      mbar_init(bar_tempty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(kBTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  const int nk = (prm.K + kBK - 1) / kBK;
+  const int ntiles = prm.m_blocks * prm.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / prm.n_tiles) * kBM, n0 = (tile % prm.n_tiles) * kBN;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = (int)(it % kBStages);
+          const uint32_t ph = (it / kBStages) & 1u;
+          mbar_wait(bar_empty(s), ph ^ 1u);  // first lap: passes at once
+          const uint32_t st = base + (uint32_t)s * kStageBytes;
+          mbar_expect_tx(bar_full(s), (uint32_t)(kRawBytes + 3 * kHalfBytes));
+          tma_load_2d_b(st, &tm_a, bar_full(s), kc * kBK, m0);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            tma_load_3d(st + kRawBytes + (3 + i) * kHalfBytes, &tm_b, bar_full(s), kc * kBK, n0, i);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+        const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
+        mbar_wait(bar_tempty((int)b), tph ^ 1u);  // the epilogue has drained this accumulator (first two tiles: at once)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem + b * (uint32_t)kBN;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = (int)(it % kBStages);
+          const uint32_t ph = (it / kBStages) & 1u;
+          mbar_wait(bar_full(s), ph);  // weight tiles landed
+          mbar_wait(bar_conv(s), ph);  // x tile split by all 128 converter threads
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = base + (uint32_t)s * kStageBytes + kRawBytes, b0 = a0 + 3 * kHalfBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the 64-byte swizzle row
+            const uint32_t ko = 32u * (uint32_t)k;
+            uint64_t da[3], db[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              da[i] = umma_desc_k64(a0 + (uint32_t)i * kHalfBytes + ko);
+              db[i] = umma_desc_k64(b0 + (uint32_t)i * kHalfBytes + ko);
+            }
+            // smallest terms first: (i, j) with i + j = 2, then 1, then the leading product
+            umma_bf16(acc, da[0], db[2], (kc | k) != 0);
+            umma_bf16(acc, da[1], db[1], 1u);
+            umma_bf16(acc, da[2], db[0], 1u);
+            umma_bf16(acc, da[0], db[1], 1u);
+            umma_bf16(acc, da[1], db[0], 1u);
+            umma_bf16(acc, da[0], db[0], 1u);
+          }
+          umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
+        }
+        umma_commit(bar_tfull((int)b));  // accumulator complete
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------ x-tile splitter (128 threads, thread = row) ------------------
+    const int r = tid - 64;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const int s = (int)(it % kBStages);
+        const uint32_t ph = (it / kBStages) & 1u;
+        mbar_wait(bar_full(s), ph);
+        unsigned char* st = sm + (size_t)s * kStageBytes;
+        const unsigned char* src = st + (size_t)r * 128;          // 128-byte row, 16-byte pieces XOR-swizzled by (r & 7)
+        unsigned char* dst = st + kRawBytes + (size_t)r * 64;     // 64-byte rows, pieces XOR-swizzled by ((r >> 1) & 3)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 8 floats -> one 16-byte bf16 piece per term
+          const float4 u = *reinterpret_cast<const float4*>(src + (((2 * j) ^ (r & 7)) << 4));
+          const float4 v = *reinterpret_cast<const float4*>(src + (((2 * j + 1) ^ (r & 7)) << 4));
+          uint4 t0, t1, t2;
+          split8(u, v, t0, t1, t2);
+          const int pc = (j ^ ((r >> 1) & 3)) << 4;
+          *reinterpret_cast<uint4*>(dst + pc) = t0;
+          *reinterpret_cast<uint4*>(dst + kHalfBytes + pc) = t1;
+          *reinterpret_cast<uint4*>(dst + 2 * kHalfBytes + pc) = t2;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core (async proxy) reads
+        mbar_arrive(bar_conv(s));
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 6-9: TMEM lane quarters 2, 3, 0, 1) -----------
+    const int q = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int m0 = (tile / prm.n_tiles) * kBM, n0 = (tile % prm.n_tiles) * kBN;
+      const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
+      mbar_wait(bar_tfull((int)b), tph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + q * 32 + lane;
+      float* orow = prm.out + (int64_t)row * prm.N + n0;
+#pragma unroll 1
+      for (int c = 0; c < kBN; c += 16) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem + b * (uint32_t)kBN + (uint32_t)c + ((uint32_t)(q * 32) << 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < prm.rows) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const int n = n0 + c + j;
+            if (n < prm.N) {  // N % 4 == 0: a 4-column piece is inside or outside as a whole
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (prm.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(prm.bias + n));
+                o.x += bb.x;
+                o.y += bb.y;
+                o.z += bb.z;
+                o.w += bb.w;
+              }
+              if (prm.relu) {
+                o.x = fmaxf(o.x, 0.f);
+                o.y = fmaxf(o.y, 0.f);
+                o.z = fmaxf(o.z, 0.f);
+                o.w = fmaxf(o.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(orow + c + j) = o;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_tempty((int)b));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kBTmemCols) : "memory");
+  }
+}
+
+// W [n] fp32 -> terms [3][n] bf16: t0 = bf16(w), t1 = bf16(w - t0), t2 = bf16(w - t0 - t1)
+__global__ void bf16_split3_kernel(const float* __restrict__ w, int64_t n, __nv_bfloat16* __restrict__ t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = w[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  const float r1 = a - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(m);
+  t[i] = h;
+  t[n + i] = m;
+  t[2 * n + i] = __float2bfloat16_rn(r2);
+}
+
+}  // namespace
+}  // namespace mvd
+
+using namespace mvd;
+
+extern "C" int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void* stream) {
+  if (!w || !terms) return MVD_ERR_NULL_POINTER;
+  if (n <= 0) return MVD_ERR_BAD_SHAPE;
+  bf16_split3_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(w, n,
+                                                                                      reinterpret_cast<__nv_bfloat16*>(terms));
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
+
+extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
+                                     int relu, float* out, void* stream) {
+  if (!x || !w_terms || !out) return MVD_ERR_NULL_POINTER;
+  if (rows <= 0 || K <= 0 || N <= 0 || rows > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
+  if (K % 8 != 0 || N % 4 != 0) return MVD_ERR_UNSUPPORTED;  // 16-byte row pitch of the bf16 terms, 16-byte output pieces
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_terms) |
+                       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias);
+  if (al & 15u) return MVD_ERR_MISALIGNED;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return MVD_ERR_NO_DEVICE;
+  alignas(64) CUtensorMap tm_a, tm_b;
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  {
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    if (enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MVD_ERR_UNSUPPORTED;
+  }
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, 3};
+    const cuuint64_t gstr[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBN, 1u};
+    if (enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_terms), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MVD_ERR_UNSUPPORTED;
+  }
+  MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
+  GbParams prm;
+  prm.bias = bias;
+  prm.out = out;
+  prm.rows = (int)rows;
+  prm.K = K;
+  prm.N = N;
+  prm.relu = relu;
+  prm.m_blocks = (int)ceil_div64(rows, kBM);
+  prm.n_tiles = (int)ceil_div64(N, kBN);
+  const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  linear_bf16x3_kernel<<<grid, kBThreads, kBSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}

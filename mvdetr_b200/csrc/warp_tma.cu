@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) warp_tma_cl_kernel(const __grid
   float* raw = reinterpret_cast<float*>(smem_raw);  // 2 x kWcRaw
   float* tr = raw + 2 * kWcRaw;                     // kWcTr
   int* s_off = reinterpret_cast<int*>(tr + kWcTr);  // [256] element offset of the north-west tap in `tr` (pixel index)
-  float* s_w = reinterpret_cast<float*>(s_off + kWtThreads);  // [4][256] tap weights (0 for pixels without a valid tap)
+  float* s_w = reinterpret_cast<float*>(s_off + kWtThreads);  // [256] float4 tap weights nw, ne, sw, se (0 if no valid tap)
   __shared__ float sT[9];
   __shared__ int s_box[4];
   __shared__ __align__(8) unsigned long long s_bar[2];
@@ -351,10 +351,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) warp_tma_cl_kernel(const __grid
 
   // per-pixel tap records for the gather (one thread = one pixel wrote them; any warp reads them)
   s_off[tid] = valid ? ((t.y0 - ymin) * bbw + (t.x0 - xmin)) : -1;
-  s_w[tid] = valid ? t.nw : 0.f;
-  s_w[kWtThreads + tid] = valid ? t.ne : 0.f;
-  s_w[2 * kWtThreads + tid] = valid ? t.sw : 0.f;
-  s_w[3 * kWtThreads + tid] = valid ? t.se : 0.f;
+  reinterpret_cast<float4*>(s_w)[tid] = valid ? make_float4(t.nw, t.ne, t.sw, t.se) : make_float4(0.f, 0.f, 0.f, 0.f);
 
   auto issue_chunk = [&](int ch) {  // one thread: channels [ch*CH, (ch+1)*CH) of the patch -> raw stage ch & 1
     const uint32_t bar = bar0 + 8u * (uint32_t)(ch & 1);
@@ -393,12 +390,25 @@ __global__ void __launch_bounds__(kWtThreads, 2) warp_tma_cl_kernel(const __grid
     if (staged) {
       mbar_wait(bar0 + 8u * (uint32_t)(ch & 1), (uint32_t)((ch >> 1) & 1));
       // ---- transpose the patch: raw [g][c][4][bw] -> tr [y*bbw + x][CH + 4] ----
+      // lanes run along the patch pixels (consecutive x read consecutive words), warps stride the channels; the two
+      // divisions per patch pixel are done once per thread and pixel slot, not per element
       const float* rp = raw + (size_t)(ch & 1) * kWcRaw;
       const int npx = bbw * bbh;
-      for (int e = tid; e < npx * CH; e += kWtThreads) {
-        const int c = e / npx, px = e - c * npx;  // lanes along the patch pixels: consecutive x read consecutive words
-        const int y = px / bbw, x = px - y * bbw;
-        tr[px * pitch + c] = rp[(((y >> 2) * CH + c) * kWtRows + (y & 3)) * bw + x];
+      const int cstride = kWtRows * bw;
+      for (int px0 = 0; px0 < npx; px0 += 4 * 32) {
+        int ro[4], to[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int px = px0 + j * 32 + lane;
+          const int y = px / bbw, x = px - y * bbw;
+          ro[j] = px < npx ? (((y >> 2) * CH) * kWtRows + (y & 3)) * bw + x : -1;
+          to[j] = px * pitch;
+        }
+        for (int c = warp; c < CH; c += kWtThreads / 32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (ro[j] >= 0) tr[to[j] + c] = rp[ro[j] + c * cstride];
+        }
       }
       __syncthreads();
       if (tid == 0 && ch + 2 < nchunks) {  // the raw stage is free again
@@ -411,7 +421,8 @@ __global__ void __launch_bounds__(kWtThreads, 2) warp_tma_cl_kernel(const __grid
       const int p = warp * 32 + it * PPI + psub;
       const int pv = ty0 + p / TW, pu = tx0 + p % TW;
       const int o = s_off[p];
-      const float wnw = s_w[p], wne = s_w[kWtThreads + p], wsw = s_w[2 * kWtThreads + p], wse = s_w[3 * kWtThreads + p];
+      const float4 w4 = reinterpret_cast<const float4*>(s_w)[p];
+      const float wnw = w4.x, wne = w4.y, wsw = w4.z, wse = w4.w;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (o >= 0) {
         float4 q0, q1, q2, q3;

@@ -14,6 +14,7 @@
 PyTorch is used for device memory and streams only; all arithmetic happens in libmvdetr_b200.so.
 """
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -90,18 +91,34 @@ def _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_loc, a
     return B, S, M, D, L, Lq, P
 
 
-_shape_cache = {}
+class _TensorCache:
+    """Derived data cached per tensor OBJECT (weak reference + version), never per address: the caching allocator hands
+    the same data_ptr to a new tensor as soon as the old one dies, so an address key would serve stale entries."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, t):
+        ent = self._d.get(id(t))
+        if ent is not None and ent[0]() is t and ent[1] == t._version:
+            return ent[2]
+        return None
+
+    def put(self, t, payload):
+        key = id(t)
+        self._d[key] = (weakref.ref(t, lambda _r, k=key, d=self._d: d.pop(k, None)), t._version, payload)
+        return payload
+
+
+_shape_cache = _TensorCache()
 
 
 def _host_shapes(spatial_shapes):
-    """Host copy of the [L,2] int64 device tensor, cached per (storage, version): one device->host read the first time
-    a shapes tensor is seen, none afterwards (keeps the autograd path CUDA-graph capturable once warmed up)."""
-    key = (spatial_shapes.device, spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape))
-    got = _shape_cache.get(key)
+    """Host copy of the [L,2] int64 device tensor, cached on the tensor object (and its version): one device->host read
+    the first time a shapes tensor is seen, none afterwards (keeps the autograd path graph-capturable once warm)."""
+    got = _shape_cache.get(spatial_shapes)
     if got is None:
-        if len(_shape_cache) > 64:
-            _shape_cache.clear()
-        got = _shape_cache[key] = spatial_shapes.tolist()
+        got = _shape_cache.put(spatial_shapes, spatial_shapes.tolist())
     return got
 
 
@@ -391,26 +408,40 @@ def _as_nhwc(x):
     return transpose_last2(x.view(N, C, H * W)).view(N, H, W, C), True
 
 
-# "tf32x3": OUR tcgen05 kernel (3xTF32 split, fp32-level accuracy) | "bf16x9" / "fp32": cuBLASLt 12.9 | "torch"
+# "bf16x3" / "tf32x3": OUR tcgen05 kernels (split operands, fp32-level accuracy) | "bf16x9" / "fp32": cuBLASLt 12.9 | "torch"
 _GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x9")
 _gemm_ws = {}
-_tf32_split_cache = {}
+_tf32_split_cache = _TensorCache()
+_bf16_split_cache = _TensorCache()
+
+
+def _bf16_split3(weight):
+    """[3, N, K] bf16 terms of an fp32 weight (t0 = bf16(w), t1 = bf16(w - t0), t2 = bf16(w - t0 - t1)), computed on the
+    device once per weight object and version."""
+    got = _bf16_split_cache.get(weight)
+    if got is None:
+        w = weight.detach()
+        terms = torch.empty((3, *w.shape), dtype=torch.bfloat16, device=w.device)
+        with _on_device(w):
+            rc = _C.lib.mvd_bf16_split3_f32(w.data_ptr(), w.numel(), terms.data_ptr(), _stream(w))
+        _C.check(rc, "mvd_bf16_split3_f32")
+        got = _bf16_split_cache.put(weight, terms)
+    return got
 
 
 def _tf32_split(weight):
-    """(hi, lo) fp32 tensors with hi = RN_tf32(weight), lo = weight - hi; computed on the device once per weight
-    version (a few hundred KB each) and cached."""
-    key = (weight.device, weight.data_ptr(), tuple(weight.shape))
-    got = _tf32_split_cache.get(key)
-    if got is None or got[0] != weight._version:
-        hi, lo = torch.empty_like(weight), torch.empty_like(weight)
-        with _on_device(weight):
-            rc = _C.lib.mvd_tf32_split_f32(weight.data_ptr(), weight.numel(), hi.data_ptr(), lo.data_ptr(), _stream(weight))
+    """(hi, lo) fp32 tensors with hi = RN_tf32(weight), lo = weight - hi; computed on the device once per weight object
+    and version (a few hundred KB each). Pass the SAME tensor object every call (a Parameter, a cached derived weight):
+    a fresh view per call is split again each time."""
+    got = _tf32_split_cache.get(weight)
+    if got is None:
+        w = weight.detach()
+        hi, lo = torch.empty_like(w), torch.empty_like(w)
+        with _on_device(w):
+            rc = _C.lib.mvd_tf32_split_f32(w.data_ptr(), w.numel(), hi.data_ptr(), lo.data_ptr(), _stream(w))
         _C.check(rc, "mvd_tf32_split_f32")
-        if len(_tf32_split_cache) > 256:
-            _tf32_split_cache.clear()
-        got = _tf32_split_cache[key] = (weight._version, hi, lo)
-    return got[1], got[2]
+        got = _tf32_split_cache.put(weight, (hi, lo))
+    return got
 
 
 def linear_available():
@@ -428,7 +459,7 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
     rows, K = x.shape
     N = weight.shape[0]
     x = x.contiguous()
-    if mode == "tf32x3":
+    if mode in ("tf32x3", "bf16x3"):
         for name, t in (("x", x), ("weight", weight), ("bias", bias)):
             if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
                 raise RuntimeError(f"linear: {name} must be a contiguous fp32 CUDA tensor")
@@ -436,10 +467,17 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
             out = torch.empty((rows, N), dtype=x.dtype, device=x.device)
         elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (rows, N)):
             raise RuntimeError("linear: out must be a contiguous fp32 CUDA tensor [rows, N]")
-        w_hi, w_lo = _tf32_split(weight.detach())
+        bp = bias.data_ptr() if bias is not None else None
+        if mode == "bf16x3" and K % 8 == 0:
+            terms = _bf16_split3(weight)
+            with _on_device(x):
+                rc = _C.lib.mvd_linear_bf16x3_f32(x.data_ptr(), terms.data_ptr(), bp, rows, K, N, 1 if relu else 0,
+                                                  out.data_ptr(), _stream(x))
+            _C.check(rc, "mvd_linear_bf16x3_f32")
+            return out
+        w_hi, w_lo = _tf32_split(weight)
         with _on_device(x):
-            rc = _C.lib.mvd_linear_tf32x3_f32(x.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(),
-                                              bias.data_ptr() if bias is not None else None, rows, K, N,
+            rc = _C.lib.mvd_linear_tf32x3_f32(x.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), bp, rows, K, N,
                                               1 if relu else 0, out.data_ptr(), _stream(x))
         _C.check(rc, "mvd_linear_tf32x3_f32")
         return out
@@ -481,6 +519,9 @@ def gemm_mode_text():
     lt = linear_available()
     if _GEMM_MODE == "torch":
         return "torch.mm fp32 (cuBLAS SIMT), explicit MVDETR_B200_GEMM=torch"
+    if _GEMM_MODE == "bf16x3":
+        return ("bf16x3: own persistent tcgen05.mma.kind::f16 kernel (3-term bf16 split in-kernel, 6 products, fp32 "
+                "accumulate in TMEM, bias/ReLU epilogue, TMA 3-stage ring), fp32-level accuracy")
     if _GEMM_MODE == "tf32x3":
         return ("tf32x3: own tcgen05.mma.kind::tf32 kernel (3xTF32 split in-kernel, fp32 accumulate in TMEM, bias/ReLU "
                 "epilogue), fp32-level accuracy")

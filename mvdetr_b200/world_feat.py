@@ -20,6 +20,7 @@ Dense layers (Linear / LayerNorm / Conv2d) stay cuBLAS / cuDNN through torch -- 
 """
 import copy
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -287,11 +288,12 @@ class DeformTransWorldFeat(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     def gemm_weights(self):
         """Conv weights reshaped for the GEMM path ((ky, kx, c_in) column order), cached until a weight changes."""
-        convs = (self.downsample[0], self.merge_linear[0], self.upsample[1])
-        key = tuple((c.weight.data_ptr(), c.weight._version) for c in convs)
-        if getattr(self, "_gw_key", None) != key:
-            flat = [c.weight.detach().permute(0, 2, 3, 1).reshape(c.weight.shape[0], -1).contiguous() for c in convs]
-            self._gw, self._gw_key = flat, key
+        ws = [c.weight for c in (self.downsample[0], self.merge_linear[0], self.upsample[1])]
+        key = getattr(self, "_gw_key", None)  # (weak refs to the source Parameters, their versions): object identity,
+        fresh = key is not None and all(r() is w and v == w._version for (r, v), w in zip(key, ws))  # never addresses
+        if not fresh:
+            self._gw = [w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous() for w in ws]
+            self._gw_key = [(weakref.ref(w), w._version) for w in ws]
         return self._gw
 
     def fast_path_ok(self, x):
@@ -307,7 +309,7 @@ class DeformTransWorldFeat(nn.Module):
     def encode_tokens(self, src, N, Hd, Wd, perm_inner_last=0):
         """src [1, N*Hd*Wd, hidden] view-major tokens -> encoder output (cell-major rows when perm_inner_last)."""
         B, _, C = src.shape
-        key = (self.lvl_embedding.data_ptr(), self.lvl_embedding._version, self.pos_embedding.data_ptr())
+        key = (id(self.lvl_embedding), self.lvl_embedding._version, id(self.pos_embedding), self.pos_embedding.device)
         if getattr(self, "_pos_key", None) != key:  # static at inference: position + level embedding, [1, N*Hd*Wd, C]
             self._pos = (self.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
                          self.lvl_embedding.detach().view([B, N, 1, C])).view([B, N * Hd * Wd, C]).contiguous()
