@@ -223,6 +223,12 @@ MVD_API int mvd_transpose_f32(const float* in, int batch, int rows, int cols, fl
  * ------------------------------------------------------------------------------------------ */
 MVD_API int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma, const float* beta,
                                   int64_t rows, int C, float eps, int64_t perm_inner, float* out, void* stream);
+/* Same, with a second output out2[r,:] = out[r,:] + pos[r,:] (pos, out2 [rows, C]; both or neither NULL; perm_inner must
+ * be 0 with them): the next encoder layer's query `with_pos_embed(src, pos)` written by the LayerNorm that produces src,
+ * replacing a separate elementwise add   ref: mvd/models/deformable_transformer.py:71-77. */
+MVD_API int mvd_add_layernorm_pos_f32(const float* x, const float* res, const float* res_bias, const float* gamma,
+                                      const float* beta, int64_t rows, int C, float eps, int64_t perm_inner, float* out,
+                                      const float* pos, float* out2, void* stream);
 
 /* In-place x[r, c] = act(x[r, c] + bias[c]) over [rows, C] (C % 4 == 0, 16-byte aligned), act = ReLU when `relu` != 0:
  * the bias (+ReLU) of a Linear layer whose GEMM ran bias-free.
@@ -336,6 +342,14 @@ MVD_API int mvd_tf32_split_f32(const float* w, int64_t n, float* hi, float* lo, 
 MVD_API int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void* stream);
 MVD_API int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
                           int relu, float* out, void* stream);
+/* Multi-GPU: the same GEMM with the all-gather fused into its epilogue. `out_mc` is the NVLink MULTICAST
+ * address of a symmetric buffer slot; results leave as multimem.st, replicated by the NVSwitch into every GPU's copy,
+ * tile by tile under the next tile's main loop (replaces GEMM -> ncclAllGather of the per-layer `value` rows,
+ * ref for the data flow: mvd/models/ops/modules/ms_deform_attn.py:96). mvd_multicast_copy_f32 does the same for a tensor
+ * produced elsewhere. Consumers on other GPUs must be separated from the producers by a cross-GPU barrier. */
+MVD_API int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
+                                    int N, int relu, float* out_mc, void* stream);
+MVD_API int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t n, void* stream);
 MVD_API int mvd_linear_tf32x3_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                           int64_t rows, int K, int N, int relu, float* out, void* stream);
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mvd_msda_fused_fwd_f32": [_p] * 8 + [_i] * 8 + [_p] * 4,
     "mvd_msda_fused_fwd_viewgrid_f32": [_p] * 6 + [_i] * 9 + [_p] * 4,
     "mvd_add_layernorm_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p],
+    "mvd_add_layernorm_pos_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p, _p, _p],
     "mvd_warp_im2col_f32": [_p, _p] + [_i] * 7 + [_p, _p],
     "mvd_upsample_im2col_f32": [_p] + [_i] * 6 + [_p, _p],
     "mvd_upsample_im2col_rows_f32": [_p] + [_i] * 8 + [_p, _p],
@@ -44,6 +45,8 @@ SIGNATURES = {
     "mvd_linear_tf32x3_f32": [_p, _p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_bf16_split3_f32": [_p, ctypes.c_int64, _p, _p],
     "mvd_linear_bf16x3_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
+    "mvd_linear_bf16x3_multicast_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
+    "mvd_multicast_copy_f32": [_p, _p, ctypes.c_int64, _p],
     "mvd_bias_act_f32": [_p, _p, ctypes.c_int64, _i, _i, _p],
     "mvd_warp_fwd_f32": [_p, _p] + [_i] * 6 + [_p, _i, _p],
     "mvd_warp_tma_f32": [_p, _p] + [_i] * 6 + [_p, _i, _i, _p],

@@ -22,8 +22,8 @@
 //               free 16-byte reads of the 128B-swizzled source and 16-byte writes of the 64B-swizzled destinations);
 //   warp 1      one thread issues 2 k-steps x 6 tcgen05.mma.kind::f16 (M 128, N 128, K 16) per chunk, commits the stage
 //               back to the producer, and after the last chunk commits the accumulator to the epilogue;
-//   warps 6-9   epilogue: tcgen05.ld 32 lanes x 16 columns at a time, + bias, ReLU, 16-byte stores of their own rows,
-//               overlapping the next tile's main loop (two 128-column accumulators in tensor memory).
+//   warps 6-9   epilogue: tcgen05.ld 32 lanes x 16 columns of both accumulators, sum + bias, ReLU, 16-byte stores of
+//               their own rows, overlapping the next tile's main loop (2 x 2 x 128 accumulator columns in tensor memory).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -38,13 +38,14 @@ constexpr int kRawBytes = kBM * kBK * 4;      // 16 KB fp32 x tile
 constexpr int kHalfBytes = kBM * kBK * 2;     // 8 KB bf16 tile (x split or weight term)
 constexpr int kStageBytes = kRawBytes + 6 * kHalfBytes;  // 64 KB
 constexpr int kBSmem = kBStages * kStageBytes + 1024;    // + slack for 1024-byte alignment
-constexpr uint32_t kBTmemCols = 256;          // two 128-column fp32 accumulators
+constexpr uint32_t kBTmemCols = 512;          // 2 buffers x {leading product, small terms} x 128 fp32 columns
 
 struct GbParams {
   const float* bias;  // nullable
   float* out;
   int rows, K, N, relu;
   int m_blocks, n_tiles;
+  int multicast;  // != 0: `out` is an NVLink multicast address (multimem.st: the NVSwitch replicates every store to all GPUs)
 };
 
 __device__ __forceinline__ void tma_load_2d_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -88,20 +89,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// three-term bf16 split of 8 consecutive floats -> one 16-byte piece per term
+// three-term bf16 split of 2 floats: packed conversions (one cvt.rn.bf16x2.f32 per term and PAIR), the bf16 values are
+// widened back with a shift / mask (exact), the residuals are exact fp32 subtractions
+__device__ __forceinline__ void split2(float a, float b, uint32_t& t0, uint32_t& t1, uint32_t& t2) {
+  t0 = pack_bf16(a, b);  // low half = bf16(a), high half = bf16(b)
+  const float ra = a - __uint_as_float(t0 << 16), rb = b - __uint_as_float(t0 & 0xffff0000u);
+  t1 = pack_bf16(ra, rb);
+  t2 = pack_bf16(ra - __uint_as_float(t1 << 16), rb - __uint_as_float(t1 & 0xffff0000u));
+}
+
+// 8 consecutive floats -> one 16-byte piece per term
 __device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& t0, uint4& t1, uint4& t2) {
-  const float a[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
-  float h[8], m[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    h[i] = __bfloat162float(__float2bfloat16_rn(a[i]));
-    const float r1 = a[i] - h[i];  // exact
-    m[i] = __bfloat162float(__float2bfloat16_rn(r1));
-    l[i] = r1 - m[i];              // exact; rounded to bf16 by the pack below
-  }
-  t0 = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-  t1 = make_uint4(pack_bf16(m[0], m[1]), pack_bf16(m[2], m[3]), pack_bf16(m[4], m[5]), pack_bf16(m[6], m[7]));
-  t2 = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+  split2(u.x, u.y, t0.x, t1.x, t2.x);
+  split2(u.z, u.w, t0.y, t1.y, t2.y);
+  split2(v.x, v.y, t0.z, t1.z, t2.z);
+  split2(v.z, v.w, t0.w, t1.w, t2.w);
 }
 
 __global__ void __launch_bounds__(kBThreads, 1)
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(kBThreads, 1)
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long s_bar[3 * kBStages + 4];  // full, conv, empty per stage; tfull[2], tempty[2]
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[kBN];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -176,7 +179,11 @@ __global__ void __launch_bounds__(kBThreads, 1)
         const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
         mbar_wait(bar_tempty((int)b), tph ^ 1u);  // the epilogue has drained this accumulator (first two tiles: at once)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem + b * (uint32_t)kBN;
+        // two accumulators per tile: the tensor core's fp32 accumulation truncates (~0.5 ulp of the ACCUMULATOR per
+        // instruction, r02e: error grew with the number of MMAs, 6 per k-step). The leading product a0*b0 gets its own
+        // accumulator (K/16 additions); the five small products (2^-8 and below) go to a second one whose rounding is
+        // 2^-8 smaller. The epilogue adds the two in fp32.
+        const uint32_t acc_hi = tmem + b * (uint32_t)(2 * kBN), acc_lo = acc_hi + (uint32_t)kBN;
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = (int)(it % kBStages);
           const uint32_t ph = (it / kBStages) & 1u;
@@ -194,12 +201,12 @@ __global__ void __launch_bounds__(kBThreads, 1)
               db[i] = umma_desc_k64(b0 + (uint32_t)i * kHalfBytes + ko);
             }
             // smallest terms first: (i, j) with i + j = 2, then 1, then the leading product
-            umma_bf16(acc, da[0], db[2], (kc | k) != 0);
-            umma_bf16(acc, da[1], db[1], 1u);
-            umma_bf16(acc, da[2], db[0], 1u);
-            umma_bf16(acc, da[0], db[1], 1u);
-            umma_bf16(acc, da[1], db[0], 1u);
-            umma_bf16(acc, da[0], db[0], 1u);
+            umma_bf16(acc_lo, da[0], db[2], (kc | k) != 0);
+            umma_bf16(acc_lo, da[1], db[1], 1u);
+            umma_bf16(acc_lo, da[2], db[0], 1u);
+            umma_bf16(acc_lo, da[0], db[1], 1u);
+            umma_bf16(acc_lo, da[1], db[0], 1u);
+            umma_bf16(acc_hi, da[0], db[0], (kc | k) != 0);
           }
           umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
         }
@@ -244,37 +251,51 @@ __global__ void __launch_bounds__(kBThreads, 1)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + q * 32 + lane;
       float* orow = prm.out + (int64_t)row * prm.N + n0;
+      // bias of this column tile -> shared memory once (every thread needs all 128 values of its row)
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done with s_bias
+      {
+        const int et = tid - 192, n = n0 + et;
+        s_bias[et] = (prm.bias && n < prm.N) ? __ldg(prm.bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t t_hi = tmem + b * (uint32_t)(2 * kBN) + ((uint32_t)(q * 32) << 16), t_lo = t_hi + (uint32_t)kBN;
 #pragma unroll 1
       for (int c = 0; c < kBN; c += 16) {
-        uint32_t v[16];
-        const uint32_t taddr = tmem + b * (uint32_t)kBN + (uint32_t)c + ((uint32_t)(q * 32) << 16);
+        uint32_t v[16], w[16];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(taddr));
+            : "r"(t_hi + (uint32_t)c));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+              "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+            : "r"(t_lo + (uint32_t)c));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row < prm.rows) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const int n = n0 + c + j;
             if (n < prm.N) {  // N % 4 == 0: a 4-column piece is inside or outside as a whole
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                     __uint_as_float(v[j + 3]));
-              if (prm.bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(prm.bias + n));
-                o.x += bb.x;
-                o.y += bb.y;
-                o.z += bb.z;
-                o.w += bb.w;
-              }
+              const float4 bb = *reinterpret_cast<const float4*>(s_bias + c + j);
+              float4 o;
+              o.x = (__uint_as_float(v[j]) + __uint_as_float(w[j])) + bb.x;
+              o.y = (__uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1])) + bb.y;
+              o.z = (__uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2])) + bb.z;
+              o.w = (__uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3])) + bb.w;
               if (prm.relu) {
                 o.x = fmaxf(o.x, 0.f);
                 o.y = fmaxf(o.y, 0.f);
                 o.z = fmaxf(o.z, 0.f);
                 o.w = fmaxf(o.w, 0.f);
               }
-              *reinterpret_cast<float4*>(orow + c + j) = o;
+              if (prm.multicast)  // fused all-gather: one store, delivered to this row's slot on every GPU of the group
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c + j), "f"(o.x),
+                             "f"(o.y), "f"(o.z), "f"(o.w)
+                             : "memory");
+              else
+                *reinterpret_cast<float4*>(orow + c + j) = o;
             }
           }
         }
@@ -318,8 +339,8 @@ extern "C" int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void*
   return MVD_OK;
 }
 
-extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
-                                     int relu, float* out, void* stream) {
+static int linear_bf16x3(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N, int relu,
+                         float* out, int multicast, void* stream) {
   if (!x || !w_terms || !out) return MVD_ERR_NULL_POINTER;
   if (rows <= 0 || K <= 0 || N <= 0 || rows > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
   if (K % 8 != 0 || N % 4 != 0) return MVD_ERR_UNSUPPORTED;  // 16-byte row pitch of the bf16 terms, 16-byte output pieces
@@ -358,9 +379,52 @@ extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const 
   prm.relu = relu;
   prm.m_blocks = (int)ceil_div64(rows, kBM);
   prm.n_tiles = (int)ceil_div64(N, kBN);
+  prm.multicast = multicast;
   const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
   linear_bf16x3_kernel<<<grid, kBThreads, kBSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
+
+extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
+                                     int relu, float* out, void* stream) {
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out, 0, stream);
+}
+
+// Same GEMM whose epilogue IS the all-gather: `out_mc` is the NVLink multicast mapping of a symmetric buffer (every GPU
+// of the group maps the same physical layout); each 16-byte piece of the result leaves as one multimem.st that the
+// NVSwitch replicates into every GPU's copy, tile by tile while the main loop of the next tile runs. The caller
+// separates producers from consumers with a cross-GPU barrier (mvdetr_b200/sharded.py).
+extern "C" int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
+                                               int N, int relu, float* out_mc, void* stream) {
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out_mc, 1, stream);
+}
+
+namespace mvd {
+namespace {
+__global__ void multicast_copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst_mc, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_mc + i), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+}
+}  // namespace
+}  // namespace mvd
+
+// dst_mc[i] = src[i] on every GPU of the multicast group (n floats, n % 4 == 0, 16-byte aligned): the all-gather of a
+// tensor whose producer is not one of the kernels above.
+extern "C" int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t n, void* stream) {
+  if (!src || !dst_mc) return MVD_ERR_NULL_POINTER;
+  if (n <= 0 || (n & 3)) return MVD_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_mc)) & 15u) return MVD_ERR_MISALIGNED;
+  const int64_t n4 = n / 4;
+  const int64_t want = ceil_div64(n4, 256);
+  const int blocks = (int)(want > (int64_t)kNumSMs * 8 ? (int64_t)kNumSMs * 8 : want);
+  multicast_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src),
+                                                                  reinterpret_cast<float4*>(dst_mc), n4);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
 }

@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
                                                             const float* __restrict__ res_bias,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int64_t rows, int C,
-                                                            float eps, int64_t perm_inner, float* __restrict__ out) {
+                                                            float eps, int64_t perm_inner, float* __restrict__ out,
+                                                            const float* __restrict__ pos, float* __restrict__ out2) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -72,6 +73,10 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
       o.z = (v[k].z - mean) * rstd * g.z + b.z;
       o.w = (v[k].w - mean) * rstd * g.w + b.w;
       orow[i] = o;
+      if (out2) {  // second output: the next layer's query, out + position embedding (deformable_transformer.py:71-77)
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pos + row * C) + i);
+        reinterpret_cast<float4*>(out2 + row * C)[i] = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
+      }
     }
   }
 }
@@ -112,10 +117,13 @@ extern "C" int mvd_bias_act_f32(float* x, const float* bias, int64_t rows, int C
   return MVD_OK;
 }
 
-extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma,
-                                     const float* beta, int64_t rows, int C, float eps, int64_t perm_inner,
-                                     float* out, void* stream) {
+extern "C" int mvd_add_layernorm_pos_f32(const float* x, const float* res, const float* res_bias, const float* gamma,
+                                         const float* beta, int64_t rows, int C, float eps, int64_t perm_inner,
+                                         float* out, const float* pos, float* out2, void* stream) {
   if (!x || !gamma || !beta || !out) return MVD_ERR_NULL_POINTER;
+  if ((pos == nullptr) != (out2 == nullptr)) return MVD_ERR_NULL_POINTER;
+  if (out2 && perm_inner > 0) return MVD_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(out2)) & 15u) return MVD_ERR_MISALIGNED;
   if (rows <= 0 || C <= 0) return MVD_ERR_BAD_SHAPE;
   if ((C & 3) || C > 1024) return MVD_ERR_UNSUPPORTED;
   const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
@@ -129,13 +137,19 @@ extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const flo
   const int64_t blocks = ceil_div64(rows, 8);
   if (blocks > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
   if (C <= 128)
-    add_layernorm_kernel<1><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
+    add_layernorm_kernel<1><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out, pos, out2);
   else if (C <= 256)
-    add_layernorm_kernel<2><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
+    add_layernorm_kernel<2><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out, pos, out2);
   else if (C <= 512)
-    add_layernorm_kernel<4><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
+    add_layernorm_kernel<4><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out, pos, out2);
   else
-    add_layernorm_kernel<8><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out);
+    add_layernorm_kernel<8><<<(int)blocks, 256, 0, st>>>(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out, pos, out2);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
+}
+
+extern "C" int mvd_add_layernorm_f32(const float* x, const float* res, const float* res_bias, const float* gamma,
+                                     const float* beta, int64_t rows, int C, float eps, int64_t perm_inner,
+                                     float* out, void* stream) {
+  return mvd_add_layernorm_pos_f32(x, res, res_bias, gamma, beta, rows, C, eps, perm_inner, out, nullptr, nullptr, stream);
 }

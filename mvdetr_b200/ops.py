@@ -293,11 +293,12 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     return (out, attn, loc) if want_aux else out
 
 
-def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None, perm_inner=0):
+def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None, perm_inner=0, pos=None):
     """LayerNorm(x + (res + res_bias)) over the last dim in one kernel (inference glue of the encoder layer,
     ref: multiview_detector/models/deformable_transformer.py:79-80,84-85). res may be None; res_bias [C] is the bias
     of the Linear that produced `res` when that GEMM was run bias-free. perm_inner > 0: rows [outer][inner] are written
-    as [inner][outer] (same shape returned; see mvd_add_layernorm_f32)."""
+    as [inner][outer] (same shape returned; see mvd_add_layernorm_f32). pos (same shape as x): additionally returns
+    out + pos, the next layer's query -> (out, out + pos)."""
     C = x.shape[-1]
     for name, t in (("x", x), ("res", res), ("weight", weight), ("bias", bias), ("res_bias", res_bias)):
         if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
@@ -305,13 +306,19 @@ def add_layer_norm(x, res, weight, bias, eps=1e-5, res_bias=None, perm_inner=0):
     if res is not None and res.shape != x.shape:
         raise RuntimeError("add_layer_norm: x and res must have the same shape")
     out = torch.empty_like(x)
+    out2 = None
+    if pos is not None:
+        if not (pos.is_cuda and pos.is_contiguous() and pos.dtype == torch.float32 and pos.numel() == x.numel()):
+            raise RuntimeError("add_layer_norm: pos must be a contiguous fp32 CUDA tensor with x's element count")
+        out2 = torch.empty_like(x)
     with _on_device(x):
-        rc = _C.lib.mvd_add_layernorm_f32(x.data_ptr(), res.data_ptr() if res is not None else None,
-                                          res_bias.data_ptr() if res_bias is not None else None, weight.data_ptr(),
-                                          bias.data_ptr(), x.numel() // C, C, float(eps), int(perm_inner),
-                                          out.data_ptr(), _stream(x))
-    _C.check(rc, "mvd_add_layernorm_f32")
-    return out
+        rc = _C.lib.mvd_add_layernorm_pos_f32(x.data_ptr(), res.data_ptr() if res is not None else None,
+                                              res_bias.data_ptr() if res_bias is not None else None, weight.data_ptr(),
+                                              bias.data_ptr(), x.numel() // C, C, float(eps), int(perm_inner),
+                                              out.data_ptr(), pos.data_ptr() if pos is not None else None,
+                                              out2.data_ptr() if out2 is not None else None, _stream(x))
+    _C.check(rc, "mvd_add_layernorm_pos_f32")
+    return out if pos is None else (out, out2)
 
 
 _DST_NHWC, _SRC_NHWC = 1, 2  # MVD_WARP_* layout bits of include/mvdetr_b200.h
@@ -532,7 +539,8 @@ def gemm_mode_text():
 
 
 def pos_add_launches(layers):
-    """Launches of the query = src + pos add per frame that are OURS (0: the adds are torch elementwise kernels)."""
+    """Launches of the query = src + pos add per frame that are OURS: layers 2.. get their query from the previous
+    layer's LayerNorm kernel (no extra launch); the first layer's add is a torch elementwise kernel (not counted)."""
     return 0
 
 

@@ -170,12 +170,15 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
-                geometry=None, ref_table=None, ref_table_lm=None, perm_inner=0):
-        """perm_inner > 0 (inference fast path only): the layer's output rows leave cell-major, see add_layer_norm."""
+                geometry=None, ref_table=None, ref_table_lm=None, perm_inner=0, query=None, emit_query=False):
+        """perm_inner > 0 (inference fast path only): the layer's output rows leave cell-major, see add_layer_norm.
+        query: src + pos already formed by the previous layer's LayerNorm kernel; emit_query (inference fast path):
+        returns (out, out + pos), the next layer's query, from this layer's last LayerNorm kernel."""
         fast = (not torch.is_grad_enabled() and not self.training and src.is_cuda and src.dtype == torch.float32
                 and src.shape[-1] % 4 == 0 and src.shape[-1] <= 1024)
         defer = fast and ref_table is not None and (src.shape[-1] // self.self_attn.n_heads) in (4, 8, 16, 32, 64, 128)
-        src2 = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
+        src2 = self.self_attn(query if query is not None else self.with_pos_embed(src, pos), reference_points, src,
+                              spatial_shapes,
                               level_start_index, padding_mask, geometry=geometry, ref_table=ref_table,
                               ref_table_lm=ref_table_lm, defer_output_bias=defer)
         if fast:
@@ -185,12 +188,17 @@ class DeformableTransformerEncoderLayer(nn.Module):
                                      self.norm1.eps, res_bias=self.self_attn.output_proj.bias if defer else None)
             hidden = ops.linear(src.view(-1, src.shape[-1]), self.linear1.weight, self.linear1.bias, relu=True)
             src2 = ops.linear(hidden, self.linear2.weight).view(src.shape)
-            return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps,
-                                      res_bias=self.linear2.bias, perm_inner=perm_inner)
+            if emit_query and perm_inner == 0 and pos is not None:
+                return ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                          res_bias=self.linear2.bias, pos=pos.expand_as(src).contiguous())
+            out = ops.add_layer_norm(src, src2, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                     res_bias=self.linear2.bias, perm_inner=perm_inner)
+            return (out, None) if emit_query else out
         assert perm_inner == 0, "perm_inner is only valid on the inference fast path"
         src = self.norm1(src + self.dropout1(src2))
         src2 = self.linear2(self.dropout2(F.relu(self.linear1(src))))
-        return self.norm2(src + self.dropout3(src2))
+        out = self.norm2(src + self.dropout3(src2))
+        return (out, None) if emit_query else out
 
 
 class DeformableTransformerEncoder(nn.Module):
@@ -237,10 +245,13 @@ class DeformableTransformerEncoder(nn.Module):
             reference_points = self.get_reference_points(hw, valid_ratios, device=src.device)
         else:
             reference_points = self.reference_points.unsqueeze(0).expand(src.shape[0], -1, -1, -1, -1)
+        query = None
         for i, layer in enumerate(self.layers):
-            output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
-                           geometry=geometry, ref_table=self.ref_table, ref_table_lm=self.ref_table_lm,
-                           perm_inner=perm_inner_last if i == self.num_layers - 1 else 0)
+            last = i == self.num_layers - 1
+            res = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
+                        geometry=geometry, ref_table=self.ref_table, ref_table_lm=self.ref_table_lm,
+                        perm_inner=perm_inner_last if last else 0, query=query, emit_query=not last)
+            output, query = res if not last else (res, None)
         return output
 
 
