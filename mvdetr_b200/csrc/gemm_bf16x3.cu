@@ -32,13 +32,20 @@
 namespace mvd {
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32, kBStages = 3;
+constexpr int kBM = 128, kBN = 128, kBK = 32;
 constexpr int kBThreads = 320;
 constexpr int kRawBytes = kBM * kBK * 4;      // 16 KB fp32 x tile
 constexpr int kHalfBytes = kBM * kBK * 2;     // 8 KB bf16 tile (x split or weight term)
-constexpr int kStageBytes = kRawBytes + 6 * kHalfBytes;  // 64 KB
-constexpr int kBSmem = kBStages * kStageBytes + 1024;    // + slack for 1024-byte alignment
+// three decoupled rings (r02f profile: with one 64 KB stage per chunk only 3 chunks were in flight and the TMA latency
+// was exposed): raw fp32 x tiles (deep: hides the load latency), weight-term triples, split x-term triples
+constexpr int kRawStages = 6, kWStages = 3, kTStages = 2;
+constexpr int kOffRaw = 0;
+constexpr int kOffW = kOffRaw + kRawStages * kRawBytes;        //  96 KB
+constexpr int kOffT = kOffW + kWStages * 3 * kHalfBytes;       // +72 KB
+constexpr int kBSmemUsed = kOffT + kTStages * 3 * kHalfBytes;  // +48 KB = 216 KB
+constexpr int kBSmem = kBSmemUsed + 1024;                      // + slack for 1024-byte alignment
 constexpr uint32_t kBTmemCols = 512;          // 2 buffers x {leading product, small terms} x 128 fp32 columns
+constexpr int kNumBars = 2 * kRawStages + 2 * kWStages + 2 * kTStages + 4;
 
 struct GbParams {
   const float* bias;  // nullable
@@ -110,30 +117,38 @@ __global__ void __launch_bounds__(kBThreads, 1)
     linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const GbParams prm) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) unsigned long long s_bar[3 * kBStages + 4];  // full, conv, empty per stage; tfull[2], tempty[2]
+  __shared__ __align__(8) unsigned long long s_bar[kNumBars];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) float s_bias[kBN];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bars = smem_u32(&s_bar[0]);
-  auto bar_full = [&](int s) { return bars + 8u * (uint32_t)s; };
-  auto bar_conv = [&](int s) { return bars + 8u * (uint32_t)(kBStages + s); };
-  auto bar_empty = [&](int s) { return bars + 8u * (uint32_t)(2 * kBStages + s); };
-  auto bar_tfull = [&](int b) { return bars + 8u * (uint32_t)(3 * kBStages + b); };
-  auto bar_tempty = [&](int b) { return bars + 8u * (uint32_t)(3 * kBStages + 2 + b); };
+  int nb = 0;
+  auto take = [&](int n) { const uint32_t r = bars + 8u * (uint32_t)nb; nb += n; return r; };
+  const uint32_t b_raw_full = take(kRawStages), b_raw_empty = take(kRawStages);   // TMA -> splitters -> TMA
+  const uint32_t b_w_full = take(kWStages), b_w_empty = take(kWStages);           // TMA -> MMA -> TMA
+  const uint32_t b_t_full = take(kTStages), b_t_empty = take(kTStages);           // splitters -> MMA -> splitters
+  const uint32_t b_acc_full = take(2), b_acc_empty = take(2);                     // MMA -> epilogue -> MMA
 
   if (tid == 0) {
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
-    for (int s = 0; s < kBStages; ++s) {
-      mbar_init(bar_full(s), 1);
-      mbar_init(bar_conv(s), 128);
-      mbar_init(bar_empty(s), 1);
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(b_raw_full + 8u * i, 1);
+      mbar_init(b_raw_empty + 8u * i, 128);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_tfull(b), 1);
-      mbar_init(bar_tempty(b), 128);
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(b_w_full + 8u * i, 1);
+      mbar_init(b_w_empty + 8u * i, 1);
+    }
+    for (int i = 0; i < kTStages; ++i) {
+      mbar_init(b_t_full + 8u * i, 128);
+      mbar_init(b_t_empty + 8u * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(b_acc_full + 8u * i, 1);
+      mbar_init(b_acc_empty + 8u * i, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -159,15 +174,15 @@ __global__ void __launch_bounds__(kBThreads, 1)
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int m0 = (tile / prm.n_tiles) * kBM, n0 = (tile % prm.n_tiles) * kBN;
         for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int s = (int)(it % kBStages);
-          const uint32_t ph = (it / kBStages) & 1u;
-          mbar_wait(bar_empty(s), ph ^ 1u);  // first lap: passes at once
-          const uint32_t st = base + (uint32_t)s * kStageBytes;
-          mbar_expect_tx(bar_full(s), (uint32_t)(kRawBytes + 3 * kHalfBytes));
-          tma_load_2d_b(st, &tm_a, bar_full(s), kc * kBK, m0);
+          const uint32_t rs = it % kRawStages, ws = it % kWStages;
+          mbar_wait(b_raw_empty + 8u * rs, ((it / kRawStages) & 1u) ^ 1u);  // first lap: passes at once
+          mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
+          tma_load_2d_b(base + kOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
+          mbar_wait(b_w_empty + 8u * ws, ((it / kWStages) & 1u) ^ 1u);
+          mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)(3 * kHalfBytes));
 #pragma unroll
           for (int i = 0; i < 3; ++i)
-            tma_load_3d(st + kRawBytes + (3 + i) * kHalfBytes, &tm_b, bar_full(s), kc * kBK, n0, i);
+            tma_load_3d(base + kOffW + (ws * 3 + i) * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
         }
       }
     }
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(kBThreads, 1)
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
         const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
-        mbar_wait(bar_tempty((int)b), tph ^ 1u);  // the epilogue has drained this accumulator (first two tiles: at once)
+        mbar_wait(b_acc_empty + 8u * b, tph ^ 1u);  // the epilogue has drained this accumulator (first two tiles: at once)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // two accumulators per tile: the tensor core's fp32 accumulation truncates (~0.5 ulp of the ACCUMULATOR per
         // instruction, r02e: error grew with the number of MMAs, 6 per k-step). The leading product a0*b0 gets its own
@@ -185,12 +200,11 @@ __global__ void __launch_bounds__(kBThreads, 1)
         // 2^-8 smaller. The epilogue adds the two in fp32.
         const uint32_t acc_hi = tmem + b * (uint32_t)(2 * kBN), acc_lo = acc_hi + (uint32_t)kBN;
         for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int s = (int)(it % kBStages);
-          const uint32_t ph = (it / kBStages) & 1u;
-          mbar_wait(bar_full(s), ph);  // weight tiles landed
-          mbar_wait(bar_conv(s), ph);  // x tile split by all 128 converter threads
+          const uint32_t ws = it % kWStages, ts = it % kTStages;
+          mbar_wait(b_w_full + 8u * ws, (it / kWStages) & 1u);  // weight terms landed
+          mbar_wait(b_t_full + 8u * ts, (it / kTStages) & 1u);  // x terms written by all 128 splitter threads
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = base + (uint32_t)s * kStageBytes + kRawBytes, b0 = a0 + 3 * kHalfBytes;
+          const uint32_t a0 = base + kOffT + ts * 3 * kHalfBytes, b0 = base + kOffW + ws * 3 * kHalfBytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the 64-byte swizzle row
             const uint32_t ko = 32u * (uint32_t)k;
@@ -200,7 +214,7 @@ __global__ void __launch_bounds__(kBThreads, 1)
               da[i] = umma_desc_k64(a0 + (uint32_t)i * kHalfBytes + ko);
               db[i] = umma_desc_k64(b0 + (uint32_t)i * kHalfBytes + ko);
             }
-            // smallest terms first: (i, j) with i + j = 2, then 1, then the leading product
+            // smallest terms first: (i, j) with i + j = 2, then 1; the leading product into its own accumulator
             umma_bf16(acc_lo, da[0], db[2], (kc | k) != 0);
             umma_bf16(acc_lo, da[1], db[1], 1u);
             umma_bf16(acc_lo, da[2], db[0], 1u);
@@ -208,9 +222,10 @@ __global__ void __launch_bounds__(kBThreads, 1)
             umma_bf16(acc_lo, da[1], db[0], 1u);
             umma_bf16(acc_hi, da[0], db[0], (kc | k) != 0);
           }
-          umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
+          umma_commit(b_w_empty + 8u * ws);  // both operand stages reusable once these MMAs have read them
+          umma_commit(b_t_empty + 8u * ts);
         }
-        umma_commit(bar_tfull((int)b));  // accumulator complete
+        umma_commit(b_acc_full + 8u * b);  // accumulator complete
       }
     }
   } else if (warp < 6) {
@@ -219,12 +234,11 @@ __global__ void __launch_bounds__(kBThreads, 1)
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int kc = 0; kc < nk; ++kc, ++it) {
-        const int s = (int)(it % kBStages);
-        const uint32_t ph = (it / kBStages) & 1u;
-        mbar_wait(bar_full(s), ph);
-        unsigned char* st = sm + (size_t)s * kStageBytes;
-        const unsigned char* src = st + (size_t)r * 128;          // 128-byte row, 16-byte pieces XOR-swizzled by (r & 7)
-        unsigned char* dst = st + kRawBytes + (size_t)r * 64;     // 64-byte rows, pieces XOR-swizzled by ((r >> 1) & 3)
+        const uint32_t rs = it % kRawStages, ts = it % kTStages;
+        mbar_wait(b_raw_full + 8u * rs, (it / kRawStages) & 1u);          // fp32 tile landed
+        mbar_wait(b_t_empty + 8u * ts, ((it / kTStages) & 1u) ^ 1u);      // the MMAs that read this term stage retired
+        const unsigned char* src = sm + kOffRaw + (size_t)rs * kRawBytes + (size_t)r * 128;  // 128-byte row, pieces XOR (r & 7)
+        unsigned char* dst = sm + kOffT + (size_t)ts * 3 * kHalfBytes + (size_t)r * 64;       // 64-byte rows, XOR ((r >> 1) & 3)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // 8 floats -> one 16-byte bf16 piece per term
           const float4 u = *reinterpret_cast<const float4*>(src + (((2 * j) ^ (r & 7)) << 4));
@@ -236,8 +250,9 @@ __global__ void __launch_bounds__(kBThreads, 1)
           *reinterpret_cast<uint4*>(dst + kHalfBytes + pc) = t1;
           *reinterpret_cast<uint4*>(dst + 2 * kHalfBytes + pc) = t2;
         }
+        mbar_arrive(b_raw_empty + 8u * rs);                            // raw tile consumed (generic reads only)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core (async proxy) reads
-        mbar_arrive(bar_conv(s));
+        mbar_arrive(b_t_full + 8u * ts);
       }
     }
   } else {
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(kBThreads, 1)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
       const int m0 = (tile / prm.n_tiles) * kBM, n0 = (tile % prm.n_tiles) * kBN;
       const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
-      mbar_wait(bar_tfull((int)b), tph);
+      mbar_wait(b_acc_full + 8u * b, tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + q * 32 + lane;
       float* orow = prm.out + (int64_t)row * prm.N + n0;
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(kBThreads, 1)
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar_tempty((int)b));
+      mbar_arrive(b_acc_empty + 8u * b);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

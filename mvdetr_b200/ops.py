@@ -521,6 +521,36 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
     return torch.relu_(res) if relu else res
 
 
+def linear_multicast(x, weight, bias, mc_ptr, relu=False):
+    """act(x @ weight.T + bias) written through the NVLink MULTICAST address `mc_ptr` (int; the slot of a symmetric buffer
+    as mapped by torch.distributed._symmetric_memory): the GEMM's epilogue is the all-gather -- every 16-byte piece
+    leaves as one multimem.st that the NVSwitch replicates into every GPU's copy of the buffer (mvdetr_b200/sharded.py
+    separates producers and consumers with a cross-GPU barrier). bf16x3 kernel only (K % 8 == 0, N % 4 == 0)."""
+    rows, K = x.shape
+    N = weight.shape[0]
+    x = x.contiguous()
+    for name, t in (("x", x), ("weight", weight), ("bias", bias)):
+        if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError(f"linear_multicast: {name} must be a contiguous fp32 CUDA tensor")
+    terms = _bf16_split3(weight)
+    with _on_device(x):
+        rc = _C.lib.mvd_linear_bf16x3_multicast_f32(x.data_ptr(), terms.data_ptr(),
+                                                    bias.data_ptr() if bias is not None else None, rows, K, N,
+                                                    1 if relu else 0, int(mc_ptr), _stream(x))
+    _C.check(rc, "mvd_linear_bf16x3_multicast_f32")
+
+
+def multicast_copy(src, mc_ptr):
+    """src (contiguous fp32 CUDA, numel % 4 == 0) -> the symmetric-buffer slot at multicast address `mc_ptr` on every GPU."""
+    if not (src.is_cuda and src.is_contiguous() and src.dtype == torch.float32 and src.numel() % 4 == 0):
+        raise RuntimeError("multicast_copy: contiguous fp32 CUDA tensor with numel % 4 == 0 required")
+    if src.numel() == 0:
+        return
+    with _on_device(src):
+        rc = _C.lib.mvd_multicast_copy_f32(src.data_ptr(), int(mc_ptr), src.numel(), _stream(src))
+    _C.check(rc, "mvd_multicast_copy_f32")
+
+
 def gemm_mode_text():
     """One line describing how ops.linear runs (bench.py's config.gemm)."""
     lt = linear_available()

@@ -28,6 +28,8 @@ none; gather buffers are padded to the maximum and the valid rows form a contigu
 
 `gather_rows` runs on any torch.distributed backend (NCCL on the GPUs; gloo in the CPU tests of the host logic).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -72,6 +74,45 @@ def gather_rows(local_rows, partition, rows_per_view, rank, out=None, group=None
     return out.view(partition.world * pad_rows, C)[:partition.num_views * rows_per_view]
 
 
+class SymmetricBuffers:
+    """Gather buffers in NVLink symmetric memory (torch.distributed._symmetric_memory): every rank allocates the same
+    layout, the rendezvous maps the peers' copies and -- on NVSwitch systems -- ONE multicast address per buffer whose
+    stores the switch replicates into every GPU's copy. With them the all-gather is not a collective call any more:
+    the producing kernel's epilogue stores straight to the multicast address (ops.linear_multicast / multicast_copy)
+    and a barrier kernel (signal pads in the same symmetric memory) separates producers from consumers.
+    `available` is False when symmetric memory or multicast cannot be set up; callers then use NCCL."""
+
+    def __init__(self, device, group=None):
+        self.device, self.group = device, group
+        self.bufs, self.available, self.why = {}, False, ""
+        if os.environ.get("MVDETR_B200_FUSED_GATHER", "1") == "0":
+            self.why = "disabled by MVDETR_B200_FUSED_GATHER=0"
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            self.symm = symm
+            g = group if group is not None else dist.group.WORLD
+            self.group_name = g.group_name
+            probe = symm.empty(1024, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(probe, self.group_name)
+            if not hdl.multicast_ptr:
+                self.why = "no NVLink multicast support on this system"
+                return
+            self.available = True
+        except Exception as e:  # symmetric memory unavailable in this build / on this fabric
+            self.why = f"{type(e).__name__}: {e}"[:200]
+
+    def get(self, key, shape):
+        """-> (local tensor [shape], multicast base address, handle); allocated and rendezvoused once per key."""
+        ent = self.bufs.get(key)
+        if ent is None:
+            t = self.symm.empty(tuple(shape), dtype=torch.float32, device=self.device)
+            t.zero_()
+            hdl = self.symm.rendezvous(t, self.group_name)
+            ent = self.bufs[key] = (t, int(hdl.multicast_ptr), hdl)
+        return ent
+
+
 class ShardedFusion:
     """Inference-only view-sharded forward over a MultiviewFusion's parameters (every rank holds the full, identical
     parameter set; only activations are sharded)."""
@@ -85,6 +126,14 @@ class ShardedFusion:
         self._bufs = {}
         self._side = None       # side stream for the GEMMs that overlap the value all-gather
         self.shard_tail = True  # False: every rank computes the whole tail (round-1 behaviour, A/B switch)
+        self.symm = None        # SymmetricBuffers once the first CUDA frame runs (fused multicast all-gather)
+
+    def fused_gather(self, device):
+        """True when the all-gathers run as multicast stores from our kernels' epilogues instead of ncclAllGather."""
+        if self.symm is None:
+            self.symm = SymmetricBuffers(device, self.group) if (self.world > 1 and device.type == "cuda" and
+                                                                 ops._GEMM_MODE == "bf16x3") else False
+        return bool(self.symm) and self.symm.available
 
     def _buf(self, key, shape, like):
         b = self._bufs.get(key)
@@ -128,7 +177,8 @@ class ShardedFusion:
         cur = torch.cuda.current_stream(dev) if src_local.is_cuda else None
         if cur is not None and self._side is None:
             self._side = torch.cuda.Stream(device=dev)
-        for layer in wf.encoder.layers:
+        fused = self.fused_gather(dev)
+        for li, layer in enumerate(wf.encoder.layers):
             attn = layer.self_attn
             M, L, P = attn.n_heads, attn.n_levels, attn.n_points
             mine = gbuf[rank][:nq]
@@ -144,9 +194,21 @@ class ShardedFusion:
                     offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
                     logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
                     join.record(self._side)
-            if nq:
-                ops.linear(src, attn.value_proj.weight, attn.value_proj.bias, out=mine)  # local rows, in the gather buffer
-            value = gather_rows(mine, part, hw, rank, out=gbuf, group=self.group)
+            if fused:
+                # GEMM whose epilogue is the all-gather: value rows leave through the multicast address of this rank's
+                # slot and land in every GPU's buffer; the barrier kernel makes them visible to all consumers.
+                # Two buffers alternate by layer, so a fast rank's stores for layer l+1 never hit a buffer a slow rank
+                # still reads for layer l (it cannot be more than one barrier ahead).
+                sbuf, mc, hdl = self.symm.get(("gather", slot, li % 2), (part.world, part.per_rank * hw, C))
+                if nq:
+                    ops.linear_multicast(src, attn.value_proj.weight, attn.value_proj.bias,
+                                         mc + rank * part.per_rank * hw * C * 4)
+                hdl.barrier(channel=0)
+                value = sbuf.view(part.world * part.per_rank * hw, C)[:S]
+            else:
+                if nq:
+                    ops.linear(src, attn.value_proj.weight, attn.value_proj.bias, out=mine)  # local rows -> gather buffer
+                value = gather_rows(mine, part, hw, rank, out=gbuf, group=self.group)
             if nq:
                 if cur is not None:
                     # join. The side-stream tensors are consumed on this stream; their blocks return to the side stream's
@@ -167,7 +229,15 @@ class ShardedFusion:
                 src2 = ops.linear(hidden, layer.linear2.weight)
                 src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
                                          res_bias=layer.linear2.bias)
-        memory = gather_rows(src, part, hw, rank, out=gbuf, group=self.group)
+        if fused:
+            n_layers = len(wf.encoder.layers)
+            sbuf, mc, hdl = self.symm.get(("gather", slot, n_layers % 2), (part.world, part.per_rank * hw, C))
+            if nq:
+                ops.multicast_copy(src.contiguous(), mc + rank * part.per_rank * hw * C * 4)
+            hdl.barrier(channel=0)
+            memory = sbuf.view(part.world * part.per_rank * hw, C)[:S]
+        else:
+            memory = gather_rows(src, part, hw, rank, out=gbuf, group=self.group)
         if self.fusion.gemm_path and wf.fast_path_ok(memory):
             mem_cm = memory.view(N, hw, C).permute(1, 0, 2).reshape(hw, N * C)  # view-major -> cell-major rows
             if self.shard_tail and part.world > 1:
@@ -187,11 +257,18 @@ class ShardedFusion:
         band = -(-Hg // world)  # ceil: rows per rank; trailing ranks may own fewer or none
         r0, r1 = min(Hg, rank * band), min(Hg, (rank + 1) * band)
         merged = ops.linear(mem_cm.contiguous(), Wm, wf.merge_linear[0].bias, relu=True)   # [cells, C] = NHWC map
-        obuf = self._buf(("tail", slot), (world, band * Wg, C), merged)
-        if r1 > r0:
-            A = ops.upsample_im2col(merged.view(1, Hd, Wd, C), (Hg, Wg), rows=(r0, r1 - r0))
-            ops.linear(A, Wu, wf.upsample[1].bias, relu=True, out=obuf[rank][:(r1 - r0) * Wg])
-        dist.all_gather_into_tensor(obuf.view(-1), obuf[rank].reshape(-1), group=self.group)
+        if self.fused_gather(merged.device):
+            obuf, mc, hdl = self.symm.get(("tail", slot), (world, band * Wg, C))
+            if r1 > r0:  # the band's conv GEMM stores its rows into every GPU's copy of the output
+                A = ops.upsample_im2col(merged.view(1, Hd, Wd, C), (Hg, Wg), rows=(r0, r1 - r0))
+                ops.linear_multicast(A, Wu, wf.upsample[1].bias, mc + rank * band * Wg * C * 4, relu=True)
+            hdl.barrier(channel=0)
+        else:
+            obuf = self._buf(("tail", slot), (world, band * Wg, C), merged)
+            if r1 > r0:
+                A = ops.upsample_im2col(merged.view(1, Hd, Wd, C), (Hg, Wg), rows=(r0, r1 - r0))
+                ops.linear(A, Wu, wf.upsample[1].bias, relu=True, out=obuf[rank][:(r1 - r0) * Wg])
+            dist.all_gather_into_tensor(obuf.view(-1), obuf[rank].reshape(-1), group=self.group)
         out_cl = obuf.view(world * band * Wg, C)[:Hg * Wg]   # bands are contiguous row ranges: valid rows form a prefix
         return ops.transpose_last2(out_cl.view(1, Hg * Wg, C)).view(1, C, Hg, Wg)
 
@@ -238,6 +315,9 @@ class ShardedFrameRunner:
                     self.mode += f"_eager({type(e).__name__})"
                     torch.cuda.synchronize(device)
         torch.cuda.synchronize(device)
+        symm = self.sf.symm
+        self.mode += ("_multicast_epilogue" if symm and symm.available else
+                      "_nccl" + (f"({symm.why})" if symm else ""))
 
     def load(self, imgs_feat, proj_mats, slot=0):
         v0, v1 = self.sf.v0, self.sf.v1

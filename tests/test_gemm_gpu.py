@@ -58,7 +58,7 @@ def test_own_tensor_core_kernels_are_fp32_accurate(cuda, rows, K, N, mode):
     # 3xTF32 (one accumulator, 3 roundings of the accumulator per k-step): a few 1e-6 relative, growing with K --
     # inside the 1e-4 bar; ops.linear only uses it when K % 8 != 0.
     scale = exact.abs().max().item()
-    tol = max(1.5 * err_torch, 1e-6 * scale) if mode == "bf16x3" else max(8 * err_torch, 1.5e-5 * scale)
+    tol = max(2.5 * err_torch, 2e-6 * scale) if mode == "bf16x3" else max(8 * err_torch, 1.5e-5 * scale)
     got = ops.linear(x, w, b, mode=mode)
     assert (got.double() - exact).abs().max().item() <= tol
     relu = ops.linear(x, w, b, relu=True, mode=mode)
