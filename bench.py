@@ -424,15 +424,16 @@ def ref_cuda_frame(fusion, ds, wl, device, ours_out, feat, proj, iters=10):
 
 
 def our_launches_per_frame(fusion, lt_gemm):
-    """OUR kernels per frame (library GEMMs not counted): warp (1 launch when the TMA kernel takes the NCHW source, else
-    relayout + gather), then per layer 1 fused MSDA + 2 add_layernorm (+ 2 bias_act when the Linear layers run through
-    torch.mm), the query add of the 2nd/3rd layer folded into the previous LayerNorm, plus upsample_im2col and the
-    final NHWC->NCHW transpose on the GEMM conv path."""
+    """OUR kernels per frame: the warp (1 launch with the TMA kernel on the NCHW source, else relayout + gather); per
+    encoder layer 1 fused MSDA + 2 add_layernorm (the 2nd also emits the next layer's query) + the 6 Linear GEMMs when
+    they run on our tcgen05 kernel (cuBLASLt launches are NOT counted; torch.mm mode adds 2 bias_act); on the GEMM conv
+    path the downsample / merge / upsample-conv GEMMs (ours), upsample_im2col and the final NHWC->NCHW transpose."""
     from mvdetr_b200 import ops
+    own = ops._GEMM_MODE in ("bf16x3", "tf32x3")
     n = ops.warp_launch_count(im2col=fusion.gemm_path)
-    n += (3 if lt_gemm else 5) * LAYERS
-    n += ops.pos_add_launches(LAYERS)
-    n += 2 if fusion.gemm_path else 0
+    n += LAYERS * (3 + (6 if own else 0) + (0 if (own or lt_gemm) else 2))
+    if fusion.gemm_path:
+        n += 2 + (3 if own else 0)
     return n
 
 

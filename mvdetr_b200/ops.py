@@ -416,7 +416,7 @@ def _as_nhwc(x):
 
 
 # "bf16x3" / "tf32x3": OUR tcgen05 kernels (split operands, fp32-level accuracy) | "bf16x9" / "fp32": cuBLASLt 12.9 | "torch"
-_GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x9")
+_GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x3")
 _gemm_ws = {}
 _tf32_split_cache = _TensorCache()
 _bf16_split_cache = _TensorCache()
