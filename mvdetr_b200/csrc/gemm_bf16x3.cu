@@ -36,13 +36,14 @@ constexpr int kBM = 128, kBN = 128, kBK = 32;
 constexpr int kBThreads = 320;
 constexpr int kRawBytes = kBM * kBK * 4;      // 16 KB fp32 x tile
 constexpr int kHalfBytes = kBM * kBK * 2;     // 8 KB bf16 tile (x split or weight term)
-// three decoupled rings (r02f profile: with one 64 KB stage per chunk only 3 chunks were in flight and the TMA latency
-// was exposed): raw fp32 x tiles (deep: hides the load latency), weight-term triples, split x-term triples
-constexpr int kRawStages = 6, kWStages = 3, kTStages = 2;
+// three decoupled rings: raw fp32 x tiles, weight-term triples, split x-term triples (+ the epilogue warps' stages)
+constexpr int kRawStages = 4, kWStages = 3, kTStages = 2;
 constexpr int kOffRaw = 0;
-constexpr int kOffW = kOffRaw + kRawStages * kRawBytes;        //  96 KB
+constexpr int kOffW = kOffRaw + kRawStages * kRawBytes;        //  64 KB
 constexpr int kOffT = kOffW + kWStages * 3 * kHalfBytes;       // +72 KB
-constexpr int kBSmemUsed = kOffT + kTStages * 3 * kHalfBytes;  // +48 KB = 216 KB
+constexpr int kOffStage = kOffT + kTStages * 3 * kHalfBytes;   // +48 KB
+constexpr int kStagePitch = 36;                                // floats per row of an epilogue warp's 32 x 32 stage
+constexpr int kBSmemUsed = kOffStage + 4 * 32 * kStagePitch * 4;  // +18 KB = 202 KB
 constexpr int kBSmem = kBSmemUsed + 1024;                      // + slack for 1024-byte alignment
 constexpr uint32_t kBTmemCols = 512;          // 2 buffers x {leading product, small terms} x 128 fp32 columns
 constexpr int kNumBars = 2 * kRawStages + 2 * kWStages + 2 * kTStages + 4;
@@ -264,8 +265,6 @@ __global__ void __launch_bounds__(kBThreads, 1)
       const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
       mbar_wait(b_acc_full + 8u * b, tph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = m0 + q * 32 + lane;
-      float* orow = prm.out + (int64_t)row * prm.N + n0;
       // bias of this column tile -> shared memory once (every thread needs all 128 values of its row)
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done with s_bias
       {
@@ -274,43 +273,64 @@ __global__ void __launch_bounds__(kBThreads, 1)
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t t_hi = tmem + b * (uint32_t)(2 * kBN) + ((uint32_t)(q * 32) << 16), t_lo = t_hi + (uint32_t)kBN;
+      // TMEM hands every thread one ROW (lane) of the tile; stored as such, a warp instruction would write 32 separate
+      // 16-byte pieces 512 bytes apart (r02h: as multimem.st these are 16-byte NVLink packets, and the 2-GPU step got
+      // slower than with ncclAllGather). The warp's 32 x 32 sub-tile is transposed through a private shared-memory
+      // stage instead, so that 8 lanes write one 128-byte row segment: 4 full lines per store instruction.
+      float* stg = reinterpret_cast<float*>(sm + kOffStage) + (size_t)q * 32 * kStagePitch;
+      const int r0 = m0 + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < kBN; c += 16) {
-        uint32_t v[16], w[16];
+      for (int c = 0; c < kBN; c += 32) {
+        uint32_t v[32], w[32];
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(t_hi + (uint32_t)c));
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
-              "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+              "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]),
+              "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
+              "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
             : "r"(t_lo + (uint32_t)c));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < prm.rows) {
+        __syncwarp();  // the previous chunk's readers are done with the stage
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const int n = n0 + c + j;
-            if (n < prm.N) {  // N % 4 == 0: a 4-column piece is inside or outside as a whole
-              const float4 bb = *reinterpret_cast<const float4*>(s_bias + c + j);
-              float4 o;
-              o.x = (__uint_as_float(v[j]) + __uint_as_float(w[j])) + bb.x;
-              o.y = (__uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1])) + bb.y;
-              o.z = (__uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2])) + bb.z;
-              o.w = (__uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3])) + bb.w;
-              if (prm.relu) {
-                o.x = fmaxf(o.x, 0.f);
-                o.y = fmaxf(o.y, 0.f);
-                o.z = fmaxf(o.z, 0.f);
-                o.w = fmaxf(o.w, 0.f);
-              }
+        for (int j = 0; j < 32; j += 4) {  // own row, 4 columns at a time: sum of the two accumulators + bias, ReLU
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + c + j);
+          float4 o;
+          o.x = (__uint_as_float(v[j]) + __uint_as_float(w[j])) + bb.x;
+          o.y = (__uint_as_float(v[j + 1]) + __uint_as_float(w[j + 1])) + bb.y;
+          o.z = (__uint_as_float(v[j + 2]) + __uint_as_float(w[j + 2])) + bb.z;
+          o.w = (__uint_as_float(v[j + 3]) + __uint_as_float(w[j + 3])) + bb.w;
+          if (prm.relu) {
+            o.x = fmaxf(o.x, 0.f);
+            o.y = fmaxf(o.y, 0.f);
+            o.z = fmaxf(o.z, 0.f);
+            o.w = fmaxf(o.w, 0.f);
+          }
+          *reinterpret_cast<float4*>(stg + lane * kStagePitch + j) = o;  // pitch 36 floats: conflict-free both ways
+        }
+        __syncwarp();
+        const int piece = lane & 7, n = n0 + c + piece * 4;
+        if (n < prm.N) {  // N % 4 == 0: a 4-column piece is inside or outside as a whole
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i;
+            if (r0 + rr < prm.rows) {
+              const float4 o = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + piece * 4);
+              float* dst = prm.out + (int64_t)(r0 + rr) * prm.N + n;
               if (prm.multicast)  // fused all-gather: one store, delivered to this row's slot on every GPU of the group
-                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + c + j), "f"(o.x),
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x),
                              "f"(o.y), "f"(o.z), "f"(o.w)
                              : "memory");
               else
-                *reinterpret_cast<float4*>(orow + c + j) = o;
+                *reinterpret_cast<float4*>(dst) = o;
             }
           }
         }

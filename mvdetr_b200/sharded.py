@@ -16,8 +16,9 @@ contiguous view range [v0, v1):
     3x3 conv for its own band of output rows only (the band's halo is computed, not exchanged), and one ALL-GATHER of the
     [rows, C] bands puts the fused feature on every rank (rank 0's copy is the one the caller reads)
 
-Inside each layer the value all-gather runs on the compute stream while the sampling-offset / attention-logit GEMMs of
-the local queries run on a side stream (fork/join with events; both are captured into the same CUDA graph).
+Inside each layer the exchange of the value rows runs on a side stream while the compute stream runs the
+sampling-offset / attention-logit GEMMs of the local queries (fork/join with events; both streams are captured into the
+same CUDA graph).
 
 The first all-gather is the north star's "all-gather of warped world-grid features before the transformer" (the
 warped features, after the per-view conv and the per-token value projection, both of which commute with the gather).
@@ -182,18 +183,10 @@ class ShardedFusion:
             attn = layer.self_attn
             M, L, P = attn.n_heads, attn.n_levels, attn.n_points
             mine = gbuf[rank][:nq]
-            offsets = logits = None
-            if nq and cur is not None:
-                # fork: the two query GEMMs only need local rows; they overlap the value projection + all-gather
-                fork, join = torch.cuda.Event(), torch.cuda.Event()
-                fork.record(cur)
-                with torch.cuda.stream(self._side):
-                    self._side.wait_event(fork)
-                    query = src + pos
-                    # bias-free GEMMs; the biases are applied inside our kernels (world_feat.MSDeformAttn.forward)
-                    offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
-                    logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
-                    join.record(self._side)
+            # value projection first (main stream); then the exchange of the value rows runs on the side stream while
+            # the main stream computes the two query GEMMs, which only need local rows. (The GEMMs are persistent
+            # kernels that fill every SM: overlapping two of THEM gains nothing -- r02h -- but the all-gather / barrier
+            # kernels need almost no SM resources.)
             if fused:
                 # GEMM whose epilogue is the all-gather: value rows leave through the multicast address of this rank's
                 # slot and land in every GPU's buffer; the barrier kernel makes them visible to all consumers.
@@ -203,22 +196,32 @@ class ShardedFusion:
                 if nq:
                     ops.linear_multicast(src, attn.value_proj.weight, attn.value_proj.bias,
                                          mc + rank * part.per_rank * hw * C * 4)
-                hdl.barrier(channel=0)
-                value = sbuf.view(part.world * part.per_rank * hw, C)[:S]
+            elif nq:
+                ops.linear(src, attn.value_proj.weight, attn.value_proj.bias, out=mine)  # local rows -> gather buffer
+
+            def exchange():
+                if fused:
+                    hdl.barrier(channel=0)
+                    return sbuf.view(part.world * part.per_rank * hw, C)[:S]
+                return gather_rows(mine, part, hw, rank, out=gbuf, group=self.group)
+
+            if cur is not None:
+                fork, join = torch.cuda.Event(), torch.cuda.Event()
+                fork.record(cur)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(fork)
+                    value = exchange()
+                    join.record(self._side)
             else:
-                if nq:
-                    ops.linear(src, attn.value_proj.weight, attn.value_proj.bias, out=mine)  # local rows -> gather buffer
-                value = gather_rows(mine, part, hw, rank, out=gbuf, group=self.group)
+                value = exchange()
             if nq:
-                if cur is not None:
-                    # join. The side-stream tensors are consumed on this stream; their blocks return to the side stream's
-                    # pool and are only reused by the next layer's side-stream work, which starts after a fork event
-                    # recorded behind the consumer -- no record_stream needed (and none inside graph capture)
-                    cur.wait_event(join)
-                else:
-                    query = src + pos
-                    offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
-                    logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
+                query = src + pos
+                # bias-free GEMMs; the biases are applied inside our kernels (world_feat.MSDeformAttn.forward)
+                offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
+                logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
+            if cur is not None:
+                cur.wait_event(join)
+            if nq:
                 out = ops.msda_fused_forward(value.view(1, S, M, C // M), geo.shapes, geo.start, offsets, logits,
                                              table, grid_hw=(Hd, Wd), ref_table_lm=wf.encoder.ref_table_lm,
                                              off_bias=attn.sampling_offsets.bias, logit_bias=attn.attention_weights.bias)
