@@ -32,25 +32,33 @@ from . import ops
 
 
 def create_pos_embedding(img_size, num_pos_feats=64, temperature=10000, normalize=True, scale=None):
-    """Sine position embedding [1, 2*num_pos_feats, H, W] (values identical to the reference's)."""
-    if scale is not None and normalize is False:
+    """Sine position embedding [1, 2*num_pos_feats, H, W], bit-identical to the table the reference builds once in its
+    constructor (ref: multiview_detector/models/trans_world_feat.py:15-37): channel c < num_pos_feats encodes the ROW,
+    the others the COLUMN; 1-based coordinates are scaled to (0, scale], divided by temperature^(2*floor(i/2)/F) and
+    passed through sin (even i) / cos (odd i)."""
+    if scale is not None and not normalize:
         raise ValueError("normalize should be True if scale is passed")
     scale = 2 * math.pi if scale is None else scale
     H, W = int(img_size[0]), int(img_size[1])
-    ones = torch.ones([1, H, W])
-    y_embed = ones.cumsum(1, dtype=torch.float32)
-    x_embed = ones.cumsum(2, dtype=torch.float32)
-    if normalize:
-        eps = 1e-6
-        y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
-        x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
-    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
-    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
-    pos_x = x_embed[:, :, :, None] / dim_t
-    pos_y = y_embed[:, :, :, None] / dim_t
-    pos_x = torch.stack((pos_x[..., 0::2].sin(), pos_x[..., 1::2].cos()), dim=4).flatten(3)
-    pos_y = torch.stack((pos_y[..., 0::2].sin(), pos_y[..., 1::2].cos()), dim=4).flatten(3)
-    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+    F_ = int(num_pos_feats)
+    i = torch.arange(F_, dtype=torch.float32)
+    period = temperature ** (2 * torch.div(i, 2, rounding_mode="floor") / F_)
+
+    def axis_code(n):
+        coord = torch.arange(1, n + 1, dtype=torch.float32)        # what a cumulative sum of ones gives
+        if normalize:
+            coord = coord / (coord[-1] + 1e-6) * scale
+        phase = coord[:, None] / period                             # [n, F]
+        code = torch.empty_like(phase)
+        code[:, 0::2] = phase[:, 0::2].sin()
+        code[:, 1::2] = phase[:, 1::2].cos()
+        return code                                                 # [n, F]
+
+    rows = axis_code(H)[:, None, :].expand(H, W, F_)
+    cols = axis_code(W)[None, :, :].expand(H, W, F_)
+    # stored channels-last and viewed as [1, 2F, H, W], like the reference's table: flatten(2).transpose(1, 2) of it
+    # is then a contiguous [1, H*W, 2F] (DeformTransWorldFeat.forward views it)
+    return torch.cat((rows, cols), -1).unsqueeze(0).permute(0, 3, 1, 2)
 
 
 class LevelGeometry:
@@ -66,34 +74,37 @@ class LevelGeometry:
 
 
 class MSDeformAttn(nn.Module):
+    """Parameter names, shapes and initialisation of ref ops/modules/ms_deform_attn.py:31-77 (checkpoints load as is)."""
+
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         super().__init__()
-        if d_model % n_heads != 0:
-            raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
+        if d_model % n_heads:
+            raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
         self.im2col_step = 64
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
-        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
-        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
-        self.value_proj = nn.Linear(d_model, d_model)
-        self.output_proj = nn.Linear(d_model, d_model)
+        samples = n_heads * n_levels * n_points
+        for name, width in (("sampling_offsets", 2 * samples), ("attention_weights", samples),
+                            ("value_proj", d_model), ("output_proj", d_model)):
+            setattr(self, name, nn.Linear(d_model, width))
         self._reset_parameters()
 
     def _reset_parameters(self):
-        constant_(self.sampling_offsets.weight.data, 0.)
-        thetas = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
-        grid_init = torch.stack([thetas.cos(), thetas.sin()], -1)
-        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(self.n_heads, 1, 1, 2)
-        grid_init = grid_init.repeat(1, self.n_levels, self.n_points, 1)
-        for i in range(self.n_points):
-            grid_init[:, :, i, :] *= i + 1
+        """Offsets start as a ring: head m looks along angle 2*pi*m/M (scaled so the larger component is 1), point k
+        sits k + 1 pixels out, the same for every level; attention logits start at zero; projections Xavier."""
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        angle = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+        ray = torch.stack([angle.cos(), angle.sin()], -1)
+        ray = ray / ray.abs().max(-1, keepdim=True)[0]
+        steps = torch.arange(1, P + 1, dtype=torch.float32)
+        ring = (ray[:, None, None, :] * steps[None, None, :, None]).expand(M, L, P, 2)
         with torch.no_grad():
-            self.sampling_offsets.bias = nn.Parameter(grid_init.view(-1))
-        constant_(self.attention_weights.weight.data, 0.)
-        constant_(self.attention_weights.bias.data, 0.)
-        xavier_uniform_(self.value_proj.weight.data)
-        constant_(self.value_proj.bias.data, 0.)
-        xavier_uniform_(self.output_proj.weight.data)
-        constant_(self.output_proj.bias.data, 0.)
+            self.sampling_offsets.weight.zero_()
+            self.sampling_offsets.bias = nn.Parameter(ring.reshape(-1).clone())
+            self.attention_weights.weight.zero_()
+            self.attention_weights.bias.zero_()
+            for proj in (self.value_proj, self.output_proj):
+                xavier_uniform_(proj.weight)
+                proj.bias.zero_()
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None, geometry=None, ref_table=None, ref_table_lm=None, defer_output_bias=False):
@@ -136,34 +147,29 @@ class MSDeformAttn(nn.Module):
                 return ops.linear(output.view(N * Len_q, -1), self.output_proj.weight).view(N, Len_q, -1)
             return self.output_proj(output)
 
-        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
-        attention_weights = self.attention_weights(query).view(N, Len_q, M, L * P)
-        attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, M, L, P)
+        # training / autograd path: the reference module's arithmetic (ms_deform_attn.py:100-117) through the 6-argument op
         if reference_points.shape[-1] != 2:
-            raise ValueError("Last dim of reference_points must be 2, but get {} instead.".format(
-                reference_points.shape[-1]))
-        offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
-        if reference_points.dim() == 4:  # upstream Deformable-DETR layout [N, Lq, L, 2]
-            reference_points = reference_points[:, :, :, None, :]
-        sampling_locations = reference_points[:, :, None, :, :, :] \
-            + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+            raise ValueError(f"Last dim of reference_points must be 2, but get {reference_points.shape[-1]} instead.")
+        if reference_points.dim() == 4:  # upstream Deformable-DETR layout [N, Lq, L, 2]: one point per level
+            reference_points = reference_points.unsqueeze(3)
+        wh = input_spatial_shapes.flip(-1)                                              # (W_l, H_l) per level
+        offsets = self.sampling_offsets(query).view(N, Len_q, M, L, P, 2)
+        locations = reference_points.unsqueeze(2) + offsets / wh[None, None, None, :, None, :]
+        weights = F.softmax(self.attention_weights(query).view(N, Len_q, M, L * P), -1).view(N, Len_q, M, L, P)
         output = ops.MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
-                                                sampling_locations.contiguous(), attention_weights.contiguous(),
-                                                self.im2col_step)
+                                                locations.contiguous(), weights.contiguous(), self.im2col_step)
         return self.output_proj(output)
 
 
 class DeformableTransformerEncoderLayer(nn.Module):
+    """Sub-module names of ref deformable_transformer.py:55-73: self_attn, norm1, linear1, linear2, norm2 (+ dropouts)."""
+
     def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, n_levels=4, n_heads=8, n_points=4):
         super().__init__()
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
-        self.dropout1 = nn.Dropout(dropout)
-        self.norm1 = nn.LayerNorm(d_model)
-        self.linear1 = nn.Linear(d_model, d_ffn)
-        self.dropout2 = nn.Dropout(dropout)
-        self.linear2 = nn.Linear(d_ffn, d_model)
-        self.dropout3 = nn.Dropout(dropout)
-        self.norm2 = nn.LayerNorm(d_model)
+        self.linear1, self.linear2 = nn.Linear(d_model, d_ffn), nn.Linear(d_ffn, d_model)
+        self.norm1, self.norm2 = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        self.dropout1, self.dropout2, self.dropout3 = (nn.Dropout(dropout) for _ in range(3))
 
     @staticmethod
     def with_pos_embed(tensor, pos):
@@ -226,16 +232,18 @@ class DeformableTransformerEncoder(nn.Module):
 
     @staticmethod
     def get_reference_points(spatial_shapes_hw, valid_ratios, device):
-        refs = []
+        """Upstream Deformable-DETR fallback (no table given): pixel centres of every level, normalised by the valid
+        part of the level, then expressed in every level's valid ratio -> [B, sum(H*W), L, 2]
+        (ref: deformable_transformer.py:29-41)."""
+        per_level = []
         for lvl, (H_, W_) in enumerate(spatial_shapes_hw):
-            ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
-                                          torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device),
-                                          indexing="ij")
-            ref_y = ref_y.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
-            ref_x = ref_x.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
-            refs.append(torch.stack((ref_x, ref_y), -1))
-        reference_points = torch.cat(refs, 1)
-        return reference_points[:, :, None] * valid_ratios[:, None]
+            cy = torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device)
+            cx = torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device)
+            gy, gx = torch.meshgrid(cy, cx, indexing="ij")
+            x = gx.reshape(1, -1) / (valid_ratios[:, None, lvl, 0] * W_)
+            y = gy.reshape(1, -1) / (valid_ratios[:, None, lvl, 1] * H_)
+            per_level.append(torch.stack((x, y), -1))
+        return torch.cat(per_level, 1)[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
                 geometry=None, perm_inner_last=0):
@@ -361,3 +369,26 @@ class DeformTransWorldFeat(nn.Module):
         memory = self.encoder(src_flatten, geo.shapes, geo.start, valid_ratios, lvl_pos_embed_flatten, geometry=geo)
         merged_feat = self.merge_linear(memory.view(B, N, H, W, C).permute(0, 1, 4, 2, 3).reshape(B, N * C, H, W))
         return self.upsample(merged_feat)
+
+
+def from_reference(ref_world_feat):
+    """Wraps an instance of the UNMODIFIED reference `DeformTransWorldFeat` (ref: trans_world_feat.py:70-119): returns our
+    mirror built from the reference module's own hyper-parameters and SHARING its Parameter objects (no copy), so
+    `model.world_feat = from_reference(model.world_feat)` accelerates an existing reference model in place -- training
+    keeps updating the same tensors, checkpoints keep their keys."""
+    conv = ref_world_feat.downsample[0]
+    layer = ref_world_feat.encoder.layers[0]
+    attn = layer.self_attn
+    num_cam, hidden = ref_world_feat.lvl_embedding.shape
+    size = ref_world_feat.upsample[0].size
+    rp = getattr(ref_world_feat.encoder, "reference_points", None)
+    ours = DeformTransWorldFeat(num_cam, [int(v) for v in size], conv.in_channels, hidden_dim=hidden,
+                                dropout=layer.dropout1.p, nhead=attn.n_heads, dim_feedforward=layer.linear1.out_features,
+                                n_points=attn.n_points, stride=conv.stride[0], reference_points=rp)
+    for name, param in ref_world_feat.named_parameters():
+        owner = ours
+        *path, leaf = name.split(".")
+        for part in path:
+            owner = getattr(owner, part)
+        owner._parameters[leaf] = param
+    return ours.to(ref_world_feat.lvl_embedding.device).train(ref_world_feat.training)

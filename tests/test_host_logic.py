@@ -1,4 +1,7 @@
 """CPU: argument validation of the host-side mirror matches the reference's error behaviour (no GPU needed)."""
+import os
+import sys
+
 import pytest
 import torch
 
@@ -139,3 +142,32 @@ def test_conv_as_gemm_weight_layout_matches_the_im2col_definition():
     with torch.no_grad():
         wf.downsample[0].weight.mul_(2.0)
     assert torch.allclose(wf.gemm_weights()[0], 2.0 * Wd)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/multiview_detector"), reason="needs the reference checkout")
+def test_mirror_matches_the_reference_classes_and_wraps_them():
+    """Where the reference tree is importable (the build container): our mirror of the callers builds the same position
+    table, the same initial parameters from the same RNG stream and the same state_dict keys as the reference classes,
+    and from_reference() shares an existing reference module's parameters instead of copying them."""
+    import types
+    for name in ("MultiScaleDeformableAttention", "matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import numpy as np
+    import multiview_detector.models.trans_world_feat as rwf
+    from mvdetr_b200 import world_feat as wf
+    for hw, feats in (((60, 180), 64), ((7, 5), 8), ((1, 1), 4)):
+        assert torch.equal(rwf.create_pos_embedding(np.array(hw), feats), wf.create_pos_embedding(np.array(hw), feats))
+    ref_pts = torch.rand(3 * 6 * 10, 3, 4, 2)
+    kw = dict(hidden_dim=32, nhead=8, dim_feedforward=64, n_points=4, stride=2, reference_points=ref_pts)
+    torch.manual_seed(7)
+    theirs = rwf.DeformTransWorldFeat(3, [12, 20], 32, **kw)
+    torch.manual_seed(7)
+    ours = wf.DeformTransWorldFeat(3, [12, 20], 32, **kw)
+    sd_a, sd_b = theirs.state_dict(), ours.state_dict()
+    assert sorted(sd_a) == sorted(sd_b) and all(torch.equal(sd_a[k], sd_b[k]) for k in sd_a)
+    wrapped = wf.from_reference(theirs)
+    shared = dict(wrapped.named_parameters())
+    assert all(shared[n] is p for n, p in theirs.named_parameters())
