@@ -346,10 +346,13 @@ MVD_API int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const flo
  * address of a symmetric buffer slot; results leave as multimem.st, replicated by the NVSwitch into every GPU's copy,
  * tile by tile under the next tile's main loop (replaces GEMM -> ncclAllGather of the per-layer `value` rows,
  * ref for the data flow: mvd/models/ops/modules/ms_deform_attn.py:96). mvd_multicast_copy_f32 does the same for a tensor
- * produced elsewhere. Consumers on other GPUs must be separated from the producers by a cross-GPU barrier. */
+ * [rows, C] produced elsewhere; with inner > 0 it also transposes [outer][inner] rows into [inner][outer_total] rows
+ * (view-major tokens -> cell-major rows for the merge conv, ref: mvd/models/trans_world_feat.py:107-108).
+ * Consumers on other GPUs must be separated from the producers by a cross-GPU barrier. */
 MVD_API int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
                                     int N, int relu, float* out_mc, void* stream);
-MVD_API int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t n, void* stream);
+MVD_API int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t rows, int C, int64_t inner,
+                           int64_t outer_total, int64_t outer0, void* stream);
 MVD_API int mvd_linear_tf32x3_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                           int64_t rows, int K, int N, int relu, float* out, void* stream);
 

@@ -438,28 +438,42 @@ extern "C" int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_ter
 
 namespace mvd {
 namespace {
-__global__ void multicast_copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst_mc, int64_t n4) {
+// dst_mc row of local row r: r itself (inner == 0) or, with rows laid out [outer][inner] locally, the transposed position
+// (r % inner) * outer_total + outer0 + r / inner  (view-major tokens of the local views -> cell-major rows of ALL views)
+__global__ void multicast_copy_kernel(const float4* __restrict__ src, float4* __restrict__ dst_mc, int64_t rows, int c4,
+                                      int64_t inner, int64_t outer_total, int64_t outer0) {
+  const int64_t n4 = rows * c4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c4, c = i - r * c4;
+    const int64_t orow = inner > 0 ? (r % inner) * outer_total + outer0 + r / inner : r;
     const float4 v = src[i];
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_mc + i), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_mc + orow * c4 + c), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
   }
 }
 }  // namespace
 }  // namespace mvd
 
-// dst_mc[i] = src[i] on every GPU of the multicast group (n floats, n % 4 == 0, 16-byte aligned): the all-gather of a
-// tensor whose producer is not one of the kernels above.
-extern "C" int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t n, void* stream) {
+// All-gather of a tensor whose producer is not one of the kernels above: src [rows, C] (C % 4 == 0, 16-byte aligned) is
+// written through the multicast address `dst_mc` into every GPU's copy of a symmetric buffer.
+//   inner == 0: row r -> row r of dst_mc (dst_mc already points at this rank's slot);
+//   inner  > 0: local rows are [outer_local][inner]; row r -> row (r % inner) * outer_total + outer0 + r / inner of
+//               dst_mc (base of the whole buffer): view-major tokens leave cell-major, so the merge convolution over all
+//               views (ref: mvd/models/trans_world_feat.py:107-108) reads contiguous rows on every GPU without a
+//               permute-copy.
+extern "C" int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t rows, int C, int64_t inner,
+                                      int64_t outer_total, int64_t outer0, void* stream) {
   if (!src || !dst_mc) return MVD_ERR_NULL_POINTER;
-  if (n <= 0 || (n & 3)) return MVD_ERR_BAD_SHAPE;
+  if (rows <= 0 || C <= 0 || (C & 3) || inner < 0 || (inner > 0 && (rows % inner != 0 || outer_total <= 0 || outer0 < 0)))
+    return MVD_ERR_BAD_SHAPE;
   if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst_mc)) & 15u) return MVD_ERR_MISALIGNED;
-  const int64_t n4 = n / 4;
+  const int64_t n4 = rows * (C / 4);
   const int64_t want = ceil_div64(n4, 256);
   const int blocks = (int)(want > (int64_t)kNumSMs * 8 ? (int64_t)kNumSMs * 8 : want);
   multicast_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src),
-                                                                  reinterpret_cast<float4*>(dst_mc), n4);
+                                                                  reinterpret_cast<float4*>(dst_mc), rows, C / 4, inner,
+                                                                  outer_total, outer0);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
 }

@@ -540,14 +540,17 @@ def linear_multicast(x, weight, bias, mc_ptr, relu=False):
     _C.check(rc, "mvd_linear_bf16x3_multicast_f32")
 
 
-def multicast_copy(src, mc_ptr):
-    """src (contiguous fp32 CUDA, numel % 4 == 0) -> the symmetric-buffer slot at multicast address `mc_ptr` on every GPU."""
-    if not (src.is_cuda and src.is_contiguous() and src.dtype == torch.float32 and src.numel() % 4 == 0):
-        raise RuntimeError("multicast_copy: contiguous fp32 CUDA tensor with numel % 4 == 0 required")
+def multicast_copy(src, mc_ptr, inner=0, outer_total=0, outer0=0):
+    """src [rows, C] (contiguous fp32 CUDA, C % 4 == 0) -> the symmetric buffer at multicast address `mc_ptr` on every
+    GPU. inner > 0: local rows [outer_local][inner] land transposed at row (r % inner) * outer_total + outer0 + r // inner
+    (view-major tokens -> cell-major rows of all views)."""
+    if not (src.is_cuda and src.is_contiguous() and src.dtype == torch.float32 and src.dim() == 2 and src.shape[1] % 4 == 0):
+        raise RuntimeError("multicast_copy: contiguous fp32 CUDA [rows, C] with C % 4 == 0 required")
     if src.numel() == 0:
         return
     with _on_device(src):
-        rc = _C.lib.mvd_multicast_copy_f32(src.data_ptr(), int(mc_ptr), src.numel(), _stream(src))
+        rc = _C.lib.mvd_multicast_copy_f32(src.data_ptr(), int(mc_ptr), src.shape[0], src.shape[1], int(inner),
+                                           int(outer_total), int(outer0), _stream(src))
     _C.check(rc, "mvd_multicast_copy_f32")
 
 

@@ -171,14 +171,20 @@ class ShardedFusion:
             raise RuntimeError("ShardedFusion needs the compact reference table (MVDeTr's create_reference_map layout)")
         nq = src_local.shape[0]
         q0 = self.v0 * hw
-        pos = (wf.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) + wf.lvl_embedding.view(1, N, 1, C)
-               ).view(S, C)[q0:q0 + nq]
+        # position + level embedding of the local queries: static at inference, cached per parameter version
+        pkey = (id(wf.lvl_embedding), wf.lvl_embedding._version, q0, nq, dev)
+        if getattr(self, "_pos_key", None) != pkey:
+            self._pos = (wf.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
+                         wf.lvl_embedding.detach().view(1, N, 1, C)).view(S, C)[q0:q0 + nq].contiguous()
+            self._pos_key = pkey
+        pos = self._pos
         gbuf = self._buf(("gather", slot), (part.world, part.per_rank * hw, C), src_local)
         src = src_local
         cur = torch.cuda.current_stream(dev) if src_local.is_cuda else None
         if cur is not None and self._side is None:
             self._side = torch.cuda.Stream(device=dev)
         fused = self.fused_gather(dev)
+        next_query = None
         for li, layer in enumerate(wf.encoder.layers):
             attn = layer.self_attn
             M, L, P = attn.n_heads, attn.n_levels, attn.n_points
@@ -215,7 +221,7 @@ class ShardedFusion:
             else:
                 value = exchange()
             if nq:
-                query = src + pos
+                query = next_query if next_query is not None else src + pos
                 # bias-free GEMMs; the biases are applied inside our kernels (world_feat.MSDeformAttn.forward)
                 offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
                 logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
@@ -230,8 +236,22 @@ class ShardedFusion:
                                          res_bias=attn.output_proj.bias)
                 hidden = ops.linear(src, layer.linear1.weight, layer.linear1.bias, relu=True)
                 src2 = ops.linear(hidden, layer.linear2.weight)
-                src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
-                                         res_bias=layer.linear2.bias)
+                if li + 1 < len(wf.encoder.layers):  # this LayerNorm also emits the next layer's query, src + pos
+                    src, next_query = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias,
+                                                         layer.norm2.eps, res_bias=layer.linear2.bias, pos=pos)
+                else:
+                    src = ops.add_layer_norm(src, src2, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps,
+                                             res_bias=layer.linear2.bias)
+        if fused and self.fusion.gemm_path and wf.fast_path_ok(src_local):
+            # the final tokens go out CELL-major (row = ground cell, columns = (view, channel)): every rank receives the
+            # merge conv's GEMM operand directly, no permute-copy (trans_world_feat.py:107-108)
+            cbuf, mc, hdl = self.symm.get(("cells", slot), (hw, N * C))
+            if nq:
+                ops.multicast_copy(src.contiguous(), mc, inner=hw, outer_total=N, outer0=self.v0)
+            hdl.barrier(channel=0)
+            if self.shard_tail:
+                return self.sharded_tail(cbuf, Hd, Wd, slot)
+            return wf.tail_from_cell_major(cbuf, Hd, Wd)
         if fused:
             n_layers = len(wf.encoder.layers)
             sbuf, mc, hdl = self.symm.get(("gather", slot, n_layers % 2), (part.world, part.per_rank * hw, C))
