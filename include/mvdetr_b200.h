@@ -353,6 +353,14 @@ MVD_API int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_terms,
                                     int N, int relu, float* out_mc, void* stream);
 MVD_API int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t rows, int C, int64_t inner,
                            int64_t outer_total, int64_t outer0, void* stream);
+/* Same two GEMMs (same arguments, bit-identical results) with the three bf16 terms of x staged in TENSOR MEMORY by the
+ * splitter warps (tcgen05.st) and consumed by tcgen05.mma's A-from-TMEM form: 40 % less shared-memory traffic per K
+ * chunk, and for K <= 128 the terms of a 128-row block are reused by every 128-column tile of the output (x is read and
+ * split once per row block for the N = 224 / 448 / 512 layers, ref: ms_deform_attn.py:100-101, deformable_transformer.py:82). */
+MVD_API int mvd_linear_bf16x3_ts_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
+                             int relu, float* out, void* stream);
+MVD_API int mvd_linear_bf16x3_ts_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
+                                       int N, int relu, float* out_mc, void* stream);
 MVD_API int mvd_linear_tf32x3_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                           int64_t rows, int K, int N, int relu, float* out, void* stream);
 

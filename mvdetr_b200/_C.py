@@ -46,6 +46,8 @@ SIGNATURES = {
     "mvd_bf16_split3_f32": [_p, ctypes.c_int64, _p, _p],
     "mvd_linear_bf16x3_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_linear_bf16x3_multicast_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
+    "mvd_linear_bf16x3_ts_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
+    "mvd_linear_bf16x3_ts_multicast_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_multicast_copy_f32": [_p, _p, ctypes.c_int64, _i, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _p],
     "mvd_bias_act_f32": [_p, _p, ctypes.c_int64, _i, _i, _p],
     "mvd_warp_fwd_f32": [_p, _p] + [_i] * 6 + [_p, _i, _p],

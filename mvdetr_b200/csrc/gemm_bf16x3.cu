@@ -346,6 +346,292 @@ __global__ void __launch_bounds__(kBThreads, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TS variant: the x terms live in TENSOR MEMORY instead of shared memory.
+// r02i: the kernel above is bound by the shared-memory pipe, not by HBM or the tensor cores -- per 32-wide K chunk it
+// moves 176 KB through shared memory (TMA fill 40, split read 16 + write 24, UMMA operand reads 48 (x) + 48 (W)), 0.87 us
+// measured against 0.40 us of tensor time. Here the splitters write their three bf16 terms with tcgen05.st into tensor
+// memory (lane = row, one 32-bit column = two consecutive k) and the MMAs take A from there ("TS" form of tcgen05.mma):
+// 104 KB per chunk. When K <= 128 the whole row block of x stays in tensor memory (4 stages x 48 columns) and is reused by
+// every 128-column tile of the output (N = 224 / 448 / 512 layers: x is read from HBM and split ONCE per row block).
+//   tensor memory: columns 0-127 leading-product accumulator, 128-255 small-terms accumulator, 256-447 x-term stages
+//   (one accumulator buffer: the 8 epilogue warps first drain it into registers and hand it back, then do bias / ReLU /
+//   stores under the next tile's main loop)
+//   warps: 0 TMA, 1 MMA, 2-5 split (TMEM lane quarter = warp & 3), 6-13 epilogue (quarter = warp & 3, column half)
+constexpr int kTsThreads = 448;
+constexpr int kTsRawStages = 4, kTsWStages = 4, kTsAStages = 4;
+constexpr int kTsOffRaw = 0;
+constexpr int kTsOffW = kTsOffRaw + kTsRawStages * kRawBytes;            //  64 KB
+constexpr int kTsOffStage = kTsOffW + kTsWStages * 3 * kHalfBytes;       // +96 KB
+constexpr int kTsSmemUsed = kTsOffStage + 8 * 32 * kStagePitch * 4;      // +36 KB = 196 KB
+constexpr int kTsSmem = kTsSmemUsed + 1024;
+constexpr uint32_t kTsAccCols = 2 * kBN;      // leading + small-terms accumulators
+constexpr uint32_t kTsAStageCols = 48;        // 3 terms x 16 columns (32 bf16 of K per lane)
+constexpr uint32_t kTsTmemCols = 512;         // 256 + 4 x 48 = 448, rounded to a power of two
+constexpr int kTsNumBars = 2 * kTsRawStages + 2 * kTsWStages + 2 * kTsAStages + 2;
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(kIdescBf16), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(kTsThreads, 1)
+    linear_bf16x3_ts_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                            const GbParams prm) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) unsigned long long s_bar[kTsNumBars];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[kBN];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bars = smem_u32(&s_bar[0]);
+  int nb = 0;
+  auto take = [&](int n) { const uint32_t r = bars + 8u * (uint32_t)nb; nb += n; return r; };
+  const uint32_t b_raw_full = take(kTsRawStages), b_raw_empty = take(kTsRawStages);  // TMA -> splitters -> TMA
+  const uint32_t b_w_full = take(kTsWStages), b_w_empty = take(kTsWStages);          // TMA -> MMA -> TMA
+  const uint32_t b_a_full = take(kTsAStages), b_a_empty = take(kTsAStages);          // splitters -> MMA -> splitters
+  const uint32_t b_acc_full = take(1), b_acc_empty = take(1);                        // MMA -> epilogue -> MMA
+
+  if (tid == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+    for (int i = 0; i < kTsRawStages; ++i) {
+      mbar_init(b_raw_full + 8u * i, 1);
+      mbar_init(b_raw_empty + 8u * i, 128);
+    }
+    for (int i = 0; i < kTsWStages; ++i) {
+      mbar_init(b_w_full + 8u * i, 1);
+      mbar_init(b_w_empty + 8u * i, 1);
+    }
+    for (int i = 0; i < kTsAStages; ++i) {
+      mbar_init(b_a_full + 8u * i, 128);
+      mbar_init(b_a_empty + 8u * i, 1);
+    }
+    mbar_init(b_acc_full, 1);
+    mbar_init(b_acc_empty, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                 "r"(kTsTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  const int nk = (prm.K + kBK - 1) / kBK;
+  // K <= 128: the x terms of a whole row block fit the four tensor-memory stages and serve every column tile
+  const bool reuse = nk <= kTsAStages;
+  const int a_loads = reuse ? nk : prm.n_tiles * nk;  // x chunks loaded and split per row block
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      uint32_t ia = 0, iw = 0;
+      for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
+        const int m0 = mb * kBM;
+        for (int nt = 0; nt < prm.n_tiles; ++nt) {
+          const int n0 = nt * kBN;
+          for (int kc = 0; kc < nk; ++kc, ++iw) {
+            if (!reuse || nt == 0) {
+              const uint32_t rs = ia % kTsRawStages;
+              mbar_wait(b_raw_empty + 8u * rs, ((ia / kTsRawStages) & 1u) ^ 1u);  // first lap: passes at once
+              mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
+              tma_load_2d_b(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
+              ++ia;
+            }
+            const uint32_t ws = iw % kTsWStages;
+            mbar_wait(b_w_empty + 8u * ws, ((iw / kTsWStages) & 1u) ^ 1u);
+            mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)(3 * kHalfBytes));
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              tma_load_3d(base + kTsOffW + (ws * 3 + i) * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer --------------------------------------------------
+    if (lane == 0) {
+      uint32_t ia_base = 0, iw = 0, tcount = 0;
+      const uint32_t acc_hi = tmem, acc_lo = tmem + (uint32_t)kBN;
+      for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
+        for (int nt = 0; nt < prm.n_tiles; ++nt, ++tcount) {
+          mbar_wait(b_acc_empty, (tcount & 1u) ^ 1u);  // the epilogue holds the previous tile in registers (first tile: at once)
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kc = 0; kc < nk; ++kc, ++iw) {
+            const uint32_t a_idx = ia_base + (uint32_t)(reuse ? kc : nt * nk + kc);
+            const uint32_t as = a_idx % kTsAStages, ws = iw % kTsWStages;
+            if (!reuse || nt == 0) mbar_wait(b_a_full + 8u * as, (a_idx / kTsAStages) & 1u);  // x terms stored by 128 threads
+            mbar_wait(b_w_full + 8u * ws, (iw / kTsWStages) & 1u);                              // weight terms landed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = tmem + kTsAccCols + as * kTsAStageCols, b0 = base + kTsOffW + ws * 3 * kHalfBytes;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {  // UMMA K = 16 bf16: 8 tensor-memory columns of A, 32 bytes of a W row
+              uint32_t ta[3];
+              uint64_t db[3];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                ta[i] = a0 + 16u * (uint32_t)i + 8u * (uint32_t)k;
+                db[i] = umma_desc_k64(b0 + (uint32_t)i * kHalfBytes + 32u * (uint32_t)k);
+              }
+              // same order and accumulators as the kernel above: results are bit-identical
+              umma_bf16_ts(acc_lo, ta[0], db[2], (kc | k) != 0);
+              umma_bf16_ts(acc_lo, ta[1], db[1], 1u);
+              umma_bf16_ts(acc_lo, ta[2], db[0], 1u);
+              umma_bf16_ts(acc_lo, ta[0], db[1], 1u);
+              umma_bf16_ts(acc_lo, ta[1], db[0], 1u);
+              umma_bf16_ts(acc_hi, ta[0], db[0], (kc | k) != 0);
+            }
+            umma_commit(b_w_empty + 8u * ws);
+            if (!reuse || nt == prm.n_tiles - 1) umma_commit(b_a_empty + 8u * as);  // last column tile: x stage reusable
+          }
+          umma_commit(b_acc_full);
+        }
+        ia_base += (uint32_t)a_loads;
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------ x-tile splitter (thread = row = tensor-memory lane) ------------
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t t_lane = tmem + kTsAccCols + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t ia = 0;
+    for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
+      for (int l = 0; l < a_loads; ++l, ++ia) {
+        const uint32_t rs = ia % kTsRawStages, as = ia % kTsAStages;
+        mbar_wait(b_raw_full + 8u * rs, (ia / kTsRawStages) & 1u);          // fp32 tile landed
+        mbar_wait(b_a_empty + 8u * as, ((ia / kTsAStages) & 1u) ^ 1u);      // the MMAs that read this stage retired
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned char* src = sm + kTsOffRaw + (size_t)rs * kRawBytes + (size_t)r * 128;  // pieces XOR (r & 7)
+        uint32_t t0[16], t1[16], t2[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 8 floats -> 4 packed pairs per term
+          const float4 u = *reinterpret_cast<const float4*>(src + (((2 * j) ^ (r & 7)) << 4));
+          const float4 v = *reinterpret_cast<const float4*>(src + (((2 * j + 1) ^ (r & 7)) << 4));
+          split2(u.x, u.y, t0[4 * j], t1[4 * j], t2[4 * j]);
+          split2(u.z, u.w, t0[4 * j + 1], t1[4 * j + 1], t2[4 * j + 1]);
+          split2(v.x, v.y, t0[4 * j + 2], t1[4 * j + 2], t2[4 * j + 2]);
+          split2(v.z, v.w, t0[4 * j + 3], t1[4 * j + 3], t2[4 * j + 3]);
+        }
+        const uint32_t ta = t_lane + as * kTsAStageCols;
+        tmem_st16(ta, t0);
+        tmem_st16(ta + 16u, t1);
+        tmem_st16(ta + 32u, t2);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        mbar_arrive(b_raw_empty + 8u * rs);  // raw tile consumed (generic reads only)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(b_a_full + 8u * as);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 6-13) ---------------------------------------
+    const int q = warp & 3, half = (warp - 6) >> 2;  // tensor-memory lane quarter, 64-column half of the tile
+    const int et = tid - 192;
+    float* stg = reinterpret_cast<float*>(sm + kTsOffStage) + (size_t)(warp - 6) * 32 * kStagePitch;
+    const uint32_t t_hi = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64), t_lo = t_hi + (uint32_t)kBN;
+    uint32_t tcount = 0;
+    for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
+      const int r0 = mb * kBM + q * 32;
+      for (int nt = 0; nt < prm.n_tiles; ++nt, ++tcount) {
+        const int n0 = nt * kBN;
+        mbar_wait(b_acc_full, tcount & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float o[64];  // own row, own 64 columns: sum of the two accumulators
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t v[16], w[16];
+          tmem_ld16(t_hi + (uint32_t)c, v);
+          tmem_ld16(t_lo + (uint32_t)c, w);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(b_acc_empty);  // accumulator handed back: the next tile's MMAs run under the rest of this epilogue
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with s_bias
+        if (et < kBN) {
+          const int n = n0 + et;
+          s_bias[et] = (prm.bias && n < prm.N) ? __ldg(prm.bias + n) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {  // 32 x 32 sub-tiles through the warp's stage: full 128-byte row segments
+          const int c = half * 64 + cb * 32;
+          __syncwarp();  // the previous sub-tile's readers are done with the stage
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(s_bias + c + j);
+            float4 x;
+            x.x = o[cb * 32 + j] + bb.x;
+            x.y = o[cb * 32 + j + 1] + bb.y;
+            x.z = o[cb * 32 + j + 2] + bb.z;
+            x.w = o[cb * 32 + j + 3] + bb.w;
+            if (prm.relu) {
+              x.x = fmaxf(x.x, 0.f);
+              x.y = fmaxf(x.y, 0.f);
+              x.z = fmaxf(x.z, 0.f);
+              x.w = fmaxf(x.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(stg + lane * kStagePitch + j) = x;
+          }
+          __syncwarp();
+          const int piece = lane & 7, n = n0 + c + piece * 4;
+          if (n < prm.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = (lane >> 3) + 4 * i;
+              if (r0 + rr < prm.rows) {
+                const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + piece * 4);
+                float* dst = prm.out + (int64_t)(r0 + rr) * prm.N + n;
+                if (prm.multicast)
+                  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x),
+                               "f"(x.y), "f"(x.z), "f"(x.w)
+                               : "memory");
+                else
+                  *reinterpret_cast<float4*>(dst) = x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTsTmemCols) : "memory");
+  }
+}
+
 // W [n] fp32 -> terms [3][n] bf16: t0 = bf16(w), t1 = bf16(w - t0), t2 = bf16(w - t0 - t1)
 __global__ void bf16_split3_kernel(const float* __restrict__ w, int64_t n, __nv_bfloat16* __restrict__ t) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,7 +661,7 @@ extern "C" int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void*
 }
 
 static int linear_bf16x3(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N, int relu,
-                         float* out, int multicast, void* stream) {
+                         float* out, int multicast, int ts, void* stream) {
   if (!x || !w_terms || !out) return MVD_ERR_NULL_POINTER;
   if (rows <= 0 || K <= 0 || N <= 0 || rows > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
   if (K % 8 != 0 || N % 4 != 0) return MVD_ERR_UNSUPPORTED;  // 16-byte row pitch of the bf16 terms, 16-byte output pieces
@@ -404,7 +690,6 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MVD_ERR_UNSUPPORTED;
   }
-  MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
   GbParams prm;
   prm.bias = bias;
   prm.out = out;
@@ -415,16 +700,29 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
   prm.m_blocks = (int)ceil_div64(rows, kBM);
   prm.n_tiles = (int)ceil_div64(N, kBN);
   prm.multicast = multicast;
-  const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;
-  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-  linear_bf16x3_kernel<<<grid, kBThreads, kBSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+  if (ts) {  // persistent over row blocks; the column tiles of a row block run back to back on one SM
+    MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem));
+    const unsigned grid = (unsigned)(prm.m_blocks < kNumSMs ? prm.m_blocks : kNumSMs);
+    linear_bf16x3_ts_kernel<<<grid, kTsThreads, kTsSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+  } else {
+    MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
+    const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;
+    const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+    linear_bf16x3_kernel<<<grid, kBThreads, kBSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+  }
   MVD_LAUNCH_CHECK();
   return MVD_OK;
 }
 
 extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
                                      int relu, float* out, void* stream) {
-  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out, 0, stream);
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out, 0, 0, stream);
+}
+
+// Same arithmetic (bit-identical results), x terms staged in tensor memory: see linear_bf16x3_ts_kernel.
+extern "C" int mvd_linear_bf16x3_ts_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
+                                        int relu, float* out, void* stream) {
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out, 0, 1, stream);
 }
 
 // Same GEMM whose epilogue IS the all-gather: `out_mc` is the NVLink multicast mapping of a symmetric buffer (every GPU
@@ -433,7 +731,12 @@ extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const 
 // separates producers from consumers with a cross-GPU barrier (mvdetr_b200/sharded.py).
 extern "C" int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
                                                int N, int relu, float* out_mc, void* stream) {
-  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out_mc, 1, stream);
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out_mc, 1, 0, stream);
+}
+
+extern "C" int mvd_linear_bf16x3_ts_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows,
+                                                  int K, int N, int relu, float* out_mc, void* stream) {
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out_mc, 1, 1, stream);
 }
 
 namespace mvd {

@@ -417,6 +417,8 @@ def _as_nhwc(x):
 
 # "bf16x3" / "tf32x3": OUR tcgen05 kernels (split operands, fp32-level accuracy) | "bf16x9" / "fp32": cuBLASLt 12.9 | "torch"
 _GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x3")
+# bf16x3 only: x terms staged in tensor memory (tcgen05.mma with A from TMEM) instead of shared memory; same results
+_GEMM_TS = os.environ.get("MVDETR_B200_GEMM_TS", "0") == "1"
 _gemm_ws = {}
 _tf32_split_cache = _TensorCache()
 _bf16_split_cache = _TensorCache()
@@ -466,7 +468,7 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
     rows, K = x.shape
     N = weight.shape[0]
     x = x.contiguous()
-    if mode in ("tf32x3", "bf16x3"):
+    if mode in ("tf32x3", "bf16x3", "bf16x3ts", "bf16x3ss"):
         for name, t in (("x", x), ("weight", weight), ("bias", bias)):
             if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
                 raise RuntimeError(f"linear: {name} must be a contiguous fp32 CUDA tensor")
@@ -475,12 +477,13 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
         elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (rows, N)):
             raise RuntimeError("linear: out must be a contiguous fp32 CUDA tensor [rows, N]")
         bp = bias.data_ptr() if bias is not None else None
-        if mode == "bf16x3" and K % 8 == 0:
+        if mode != "tf32x3" and K % 8 == 0:
             terms = _bf16_split3(weight)
+            ts = mode == "bf16x3ts" or (mode == "bf16x3" and _GEMM_TS)   # "bf16x3ss": shared-memory operands explicitly
+            fn = _C.lib.mvd_linear_bf16x3_ts_f32 if ts else _C.lib.mvd_linear_bf16x3_f32
             with _on_device(x):
-                rc = _C.lib.mvd_linear_bf16x3_f32(x.data_ptr(), terms.data_ptr(), bp, rows, K, N, 1 if relu else 0,
-                                                  out.data_ptr(), _stream(x))
-            _C.check(rc, "mvd_linear_bf16x3_f32")
+                rc = fn(x.data_ptr(), terms.data_ptr(), bp, rows, K, N, 1 if relu else 0, out.data_ptr(), _stream(x))
+            _C.check(rc, "mvd_linear_bf16x3_ts_f32" if ts else "mvd_linear_bf16x3_f32")
             return out
         w_hi, w_lo = _tf32_split(weight)
         with _on_device(x):
@@ -533,10 +536,10 @@ def linear_multicast(x, weight, bias, mc_ptr, relu=False):
         if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
             raise RuntimeError(f"linear_multicast: {name} must be a contiguous fp32 CUDA tensor")
     terms = _bf16_split3(weight)
+    fn = _C.lib.mvd_linear_bf16x3_ts_multicast_f32 if _GEMM_TS else _C.lib.mvd_linear_bf16x3_multicast_f32
     with _on_device(x):
-        rc = _C.lib.mvd_linear_bf16x3_multicast_f32(x.data_ptr(), terms.data_ptr(),
-                                                    bias.data_ptr() if bias is not None else None, rows, K, N,
-                                                    1 if relu else 0, int(mc_ptr), _stream(x))
+        rc = fn(x.data_ptr(), terms.data_ptr(), bias.data_ptr() if bias is not None else None, rows, K, N,
+                1 if relu else 0, int(mc_ptr), _stream(x))
     _C.check(rc, "mvd_linear_bf16x3_multicast_f32")
 
 
@@ -561,7 +564,8 @@ def gemm_mode_text():
         return "torch.mm fp32 (cuBLAS SIMT), explicit MVDETR_B200_GEMM=torch"
     if _GEMM_MODE == "bf16x3":
         return ("bf16x3: own persistent tcgen05.mma.kind::f16 kernel (3-term bf16 split in-kernel, 6 products, fp32 "
-                "accumulate in TMEM, bias/ReLU epilogue, TMA 3-stage ring), fp32-level accuracy")
+                "accumulate in TMEM, bias/ReLU epilogue, TMA rings; x terms in "
+                + ("tensor memory (TS-form MMA)" if _GEMM_TS else "shared memory") + "), fp32-level accuracy")
     if _GEMM_MODE == "tf32x3":
         return ("tf32x3: own tcgen05.mma.kind::tf32 kernel (3xTF32 split in-kernel, fp32 accumulate in TMEM, bias/ReLU "
                 "epilogue), fp32-level accuracy")

@@ -44,12 +44,12 @@ def test_linear_torch_mode_needs_no_library(cuda):
 @pytest.mark.parametrize("rows,K,N", [(75600, 128, 128), (4099, 128, 448), (2048, 128, 224), (3000, 128, 512),
                                       (3000, 512, 128), (1000, 1152, 128), (77, 896, 128), (130, 36, 20), (1, 4, 4),
                                       (129, 2304, 256), (20000, 128, 128), (641, 40, 132)])
-@pytest.mark.parametrize("mode", ["bf16x3", "tf32x3"])
+@pytest.mark.parametrize("mode", ["bf16x3ss", "bf16x3ts", "tf32x3"])
 def test_own_tensor_core_kernels_are_fp32_accurate(cuda, rows, K, N, mode):
     """Our tcgen05 kernels (operands split into bf16 / tf32 terms, accumulators in tensor memory) against an fp64 product:
     bf16x3 (six products) must be as accurate as the native fp32 GEMM, the 3xTF32 variant within a small multiple of it;
     bias / ReLU epilogue, row and column tails, K not a multiple of the 32-wide chunk, many tiles per CTA."""
-    if mode == "bf16x3" and K % 8 != 0:
+    if mode != "tf32x3" and K % 8 != 0:
         pytest.skip("bf16x3 needs a 16-byte row pitch of the bf16 terms (K % 8 == 0); ops.linear then uses tf32x3")
     x, w, b = _problem(rows, K, N, rows + N + 1, cuda)
     exact = x.double() @ w.double().t() + b.double()
@@ -58,9 +58,11 @@ def test_own_tensor_core_kernels_are_fp32_accurate(cuda, rows, K, N, mode):
     # 3xTF32 (one accumulator, 3 roundings of the accumulator per k-step): a few 1e-6 relative, growing with K --
     # inside the 1e-4 bar; ops.linear only uses it when K % 8 != 0.
     scale = exact.abs().max().item()
-    tol = max(2.5 * err_torch, 2e-6 * scale) if mode == "bf16x3" else max(8 * err_torch, 1.5e-5 * scale)
+    tol = max(2.5 * err_torch, 2e-6 * scale) if mode != "tf32x3" else max(8 * err_torch, 1.5e-5 * scale)
     got = ops.linear(x, w, b, mode=mode)
     assert (got.double() - exact).abs().max().item() <= tol
+    if mode == "bf16x3ts":  # x terms in tensor memory: same products, same order, same accumulators as the shared-memory kernel
+        assert torch.equal(got, ops.linear(x, w, b, mode="bf16x3ss"))
     relu = ops.linear(x, w, b, relu=True, mode=mode)
     assert (relu.double() - exact.clamp_min(0)).abs().max().item() <= tol
     out = torch.full((rows, N), float("nan"), device=cuda)
