@@ -429,7 +429,7 @@ def our_launches_per_frame(fusion, lt_gemm):
     they run on our tcgen05 kernel (cuBLASLt launches are NOT counted; torch.mm mode adds 2 bias_act); on the GEMM conv
     path the downsample / merge / upsample-conv GEMMs (ours), upsample_im2col and the final NHWC->NCHW transpose."""
     from mvdetr_b200 import ops
-    own = ops._GEMM_MODE in ("bf16x3", "tf32x3")
+    own = ops._GEMM_MODE in ("bf16x3", "f16x2", "tf32x3")
     n = ops.warp_launch_count(im2col=fusion.gemm_path)
     n += LAYERS * (3 + (6 if own else 0) + (0 if (own or lt_gemm) else 2))
     if fusion.gemm_path:

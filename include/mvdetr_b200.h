@@ -361,6 +361,18 @@ MVD_API int mvd_linear_bf16x3_ts_f32(const float* x, const void* w_terms, const 
                              int relu, float* out, void* stream);
 MVD_API int mvd_linear_bf16x3_ts_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
                                        int N, int relu, float* out_mc, void* stream);
+/* Half the tensor work: TWO fp16 terms per operand (a = h0 + 2^-11 h1, |a - h0 - 2^-11 h1| <= 2^-24 |a|) and the THREE
+ * products h0*g0 (own accumulator), h0*g1 + h1*g0 (second accumulator, scaled by 2^-11 in the epilogue); fp16 products
+ * are exact in the tensor core's fp32 adder. Same kernel structure as the _ts_ variant (terms of x in tensor memory).
+ * Range: |x| and |w| below 65504 (fp16); beyond that the result is non-finite, never silently wrong. Same layers as
+ * above (ref: ms_deform_attn.py:96,100-101,116; deformable_transformer.py:82; trans_world_feat.py:74,82-84).
+ *   mvd_f16_split2_f32: w [n] fp32 -> terms [2][n] fp16 (device, 16-byte aligned), once per weight.
+ *   mvd_linear_f16x2_f32: x [rows, K] fp32, w_terms [2][N][K] fp16; K % 8 == 0, N % 4 == 0. */
+MVD_API int mvd_f16_split2_f32(const float* w, int64_t n, void* terms, void* stream);
+MVD_API int mvd_linear_f16x2_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
+                         int relu, float* out, void* stream);
+MVD_API int mvd_linear_f16x2_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
+                                   int N, int relu, float* out_mc, void* stream);
 MVD_API int mvd_linear_tf32x3_f32(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                           int64_t rows, int K, int N, int relu, float* out, void* stream);
 

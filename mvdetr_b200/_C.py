@@ -46,6 +46,9 @@ SIGNATURES = {
     "mvd_bf16_split3_f32": [_p, ctypes.c_int64, _p, _p],
     "mvd_linear_bf16x3_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_linear_bf16x3_multicast_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
+    "mvd_f16_split2_f32": [_p, ctypes.c_int64, _p, _p],
+    "mvd_linear_f16x2_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
+    "mvd_linear_f16x2_multicast_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_linear_bf16x3_ts_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_linear_bf16x3_ts_multicast_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_multicast_copy_f32": [_p, _p, ctypes.c_int64, _i, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _p],

@@ -26,6 +26,7 @@
 //               their own rows, overlapping the next tile's main loop (2 x 2 x 128 accumulator columns in tensor memory).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "vg_common.cuh"
 
@@ -370,15 +371,31 @@ constexpr uint32_t kTsAStageCols = 48;        // 3 terms x 16 columns (32 bf16 o
 constexpr uint32_t kTsTmemCols = 512;         // 256 + 4 x 48 = 448, rounded to a power of two
 constexpr int kTsNumBars = 2 * kTsRawStages + 2 * kTsWStages + 2 * kTsAStages + 2;
 
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+// fp16 operands (format 0) instead of bf16 (format 1): the two-term variant below
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+template <uint32_t IDESC>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(kIdescBf16), "r"(accumulate)
+      "r"(tmem_a), "l"(bdesc), "n"(IDESC), "r"(accumulate)
       : "memory");
+}
+
+// Two-term fp16 split of 2 floats, second term scaled by 2^11: a = h0 + 2^-11 h1 with |a - (h0 + 2^-11 h1)| <= 2^-24 |a|
+// (11 significant bits per term; a - h0 and the scaling are exact in fp32). fp16's range applies: |a| must stay below
+// 65504 (larger inputs give non-finite results, never silently wrong ones); below 6e-5 the absolute error is <= 2^-25.
+constexpr float kF16Scale = 2048.f;
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& t0, uint32_t& t1) {
+  const __half2 h = __floats2half2_rn(a, b);  // low half = fp16(a), high half = fp16(b)
+  const float2 f = __half22float2(h);
+  const __half2 g = __floats2half2_rn((a - f.x) * kF16Scale, (b - f.y) * kF16Scale);
+  t0 = *reinterpret_cast<const uint32_t*>(&h);
+  t1 = *reinterpret_cast<const uint32_t*>(&g);
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -399,9 +416,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+// NT = 3: three bf16 terms, six products (full fp32 range). NT = 2: two fp16 terms (second one scaled by 2^11), THREE
+// products -- half the tensor work (r02m: with 6 products the big-K layers run at ~70 % of the measured bf16 tensor peak,
+// the tensor cores are the bound); the small-terms accumulator is multiplied by 2^-11 in the epilogue.
+template <int NT>
 __global__ void __launch_bounds__(kTsThreads, 1)
-    linear_bf16x3_ts_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                            const GbParams prm) {
+    linear_split_ts_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                           const GbParams prm) {
+  constexpr uint32_t IDESC = NT == 3 ? kIdescBf16 : kIdescF16;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long s_bar[kTsNumBars];
   __shared__ uint32_t s_tmem;
@@ -471,9 +493,9 @@ __global__ void __launch_bounds__(kTsThreads, 1)
             }
             const uint32_t ws = iw % kTsWStages;
             mbar_wait(b_w_empty + 8u * ws, ((iw / kTsWStages) & 1u) ^ 1u);
-            mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)(3 * kHalfBytes));
+            mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)(NT * kHalfBytes));
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < NT; ++i)
               tma_load_3d(base + kTsOffW + (ws * 3 + i) * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
           }
         }
@@ -497,20 +519,25 @@ __global__ void __launch_bounds__(kTsThreads, 1)
             const uint32_t a0 = tmem + kTsAccCols + as * kTsAStageCols, b0 = base + kTsOffW + ws * 3 * kHalfBytes;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {  // UMMA K = 16 bf16: 8 tensor-memory columns of A, 32 bytes of a W row
-              uint32_t ta[3];
-              uint64_t db[3];
+              uint32_t ta[NT];
+              uint64_t db[NT];
 #pragma unroll
-              for (int i = 0; i < 3; ++i) {
+              for (int i = 0; i < NT; ++i) {
                 ta[i] = a0 + 16u * (uint32_t)i + 8u * (uint32_t)k;
                 db[i] = umma_desc_k64(b0 + (uint32_t)i * kHalfBytes + 32u * (uint32_t)k);
               }
-              // same order and accumulators as the kernel above: results are bit-identical
-              umma_bf16_ts(acc_lo, ta[0], db[2], (kc | k) != 0);
-              umma_bf16_ts(acc_lo, ta[1], db[1], 1u);
-              umma_bf16_ts(acc_lo, ta[2], db[0], 1u);
-              umma_bf16_ts(acc_lo, ta[0], db[1], 1u);
-              umma_bf16_ts(acc_lo, ta[1], db[0], 1u);
-              umma_bf16_ts(acc_hi, ta[0], db[0], (kc | k) != 0);
+              if constexpr (NT == 3) {
+                // same order and accumulators as the shared-memory kernel above: results are bit-identical
+                umma_ts<IDESC>(acc_lo, ta[0], db[2], (kc | k) != 0);
+                umma_ts<IDESC>(acc_lo, ta[1], db[1], 1u);
+                umma_ts<IDESC>(acc_lo, ta[2], db[0], 1u);
+                umma_ts<IDESC>(acc_lo, ta[0], db[1], 1u);
+                umma_ts<IDESC>(acc_lo, ta[1], db[0], 1u);
+              } else {
+                umma_ts<IDESC>(acc_lo, ta[0], db[1], (kc | k) != 0);  // both cross products carry the factor 2^11
+                umma_ts<IDESC>(acc_lo, ta[1], db[0], 1u);
+              }
+              umma_ts<IDESC>(acc_hi, ta[0], db[0], (kc | k) != 0);
             }
             umma_commit(b_w_empty + 8u * ws);
             if (!reuse || nt == prm.n_tiles - 1) umma_commit(b_a_empty + 8u * as);  // last column tile: x stage reusable
@@ -532,20 +559,27 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         mbar_wait(b_a_empty + 8u * as, ((ia / kTsAStages) & 1u) ^ 1u);      // the MMAs that read this stage retired
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned char* src = sm + kTsOffRaw + (size_t)rs * kRawBytes + (size_t)r * 128;  // pieces XOR (r & 7)
-        uint32_t t0[16], t1[16], t2[16];
+        uint32_t t0[16], t1[16], t2[16];  // t2: bf16 variant only
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // 8 floats -> 4 packed pairs per term
           const float4 u = *reinterpret_cast<const float4*>(src + (((2 * j) ^ (r & 7)) << 4));
           const float4 v = *reinterpret_cast<const float4*>(src + (((2 * j + 1) ^ (r & 7)) << 4));
-          split2(u.x, u.y, t0[4 * j], t1[4 * j], t2[4 * j]);
-          split2(u.z, u.w, t0[4 * j + 1], t1[4 * j + 1], t2[4 * j + 1]);
-          split2(v.x, v.y, t0[4 * j + 2], t1[4 * j + 2], t2[4 * j + 2]);
-          split2(v.z, v.w, t0[4 * j + 3], t1[4 * j + 3], t2[4 * j + 3]);
+          if constexpr (NT == 3) {
+            split2(u.x, u.y, t0[4 * j], t1[4 * j], t2[4 * j]);
+            split2(u.z, u.w, t0[4 * j + 1], t1[4 * j + 1], t2[4 * j + 1]);
+            split2(v.x, v.y, t0[4 * j + 2], t1[4 * j + 2], t2[4 * j + 2]);
+            split2(v.z, v.w, t0[4 * j + 3], t1[4 * j + 3], t2[4 * j + 3]);
+          } else {
+            split2_f16(u.x, u.y, t0[4 * j], t1[4 * j]);
+            split2_f16(u.z, u.w, t0[4 * j + 1], t1[4 * j + 1]);
+            split2_f16(v.x, v.y, t0[4 * j + 2], t1[4 * j + 2]);
+            split2_f16(v.z, v.w, t0[4 * j + 3], t1[4 * j + 3]);
+          }
         }
         const uint32_t ta = t_lane + as * kTsAStageCols;
         tmem_st16(ta, t0);
         tmem_st16(ta + 16u, t1);
-        tmem_st16(ta + 32u, t2);
+        if constexpr (NT == 3) tmem_st16(ta + 32u, t2);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         mbar_arrive(b_raw_empty + 8u * rs);  // raw tile consumed (generic reads only)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -573,7 +607,9 @@ __global__ void __launch_bounds__(kTsThreads, 1)
           tmem_ld16(t_lo + (uint32_t)c, w);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[c + j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+          for (int j = 0; j < 16; ++j)
+            o[c + j] = NT == 3 ? __uint_as_float(v[j]) + __uint_as_float(w[j])
+                               : fmaf(__uint_as_float(w[j]), 1.f / kF16Scale, __uint_as_float(v[j]));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(b_acc_empty);  // accumulator handed back: the next tile's MMAs run under the rest of this epilogue
@@ -646,10 +682,28 @@ __global__ void bf16_split3_kernel(const float* __restrict__ w, int64_t n, __nv_
   t[2 * n + i] = __float2bfloat16_rn(r2);
 }
 
+// W [n] fp32 -> terms [2][n] fp16: t0 = fp16(w), t1 = fp16((w - t0) * 2^11)
+__global__ void f16_split2_kernel(const float* __restrict__ w, int64_t n, __half* __restrict__ t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = w[i];
+  const __half h = __float2half_rn(a);
+  t[i] = h;
+  t[n + i] = __float2half_rn((a - __half2float(h)) * kF16Scale);
+}
+
 }  // namespace
 }  // namespace mvd
 
 using namespace mvd;
+
+extern "C" int mvd_f16_split2_f32(const float* w, int64_t n, void* terms, void* stream) {
+  if (!w || !terms) return MVD_ERR_NULL_POINTER;
+  if (n <= 0) return MVD_ERR_BAD_SHAPE;
+  f16_split2_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(w, n, reinterpret_cast<__half*>(terms));
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
 
 extern "C" int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void* stream) {
   if (!w || !terms) return MVD_ERR_NULL_POINTER;
@@ -661,7 +715,7 @@ extern "C" int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void*
 }
 
 static int linear_bf16x3(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N, int relu,
-                         float* out, int multicast, int ts, void* stream) {
+                         float* out, int multicast, int ts, void* stream, int terms = 3) {
   if (!x || !w_terms || !out) return MVD_ERR_NULL_POINTER;
   if (rows <= 0 || K <= 0 || N <= 0 || rows > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
   if (K % 8 != 0 || N % 4 != 0) return MVD_ERR_UNSUPPORTED;  // 16-byte row pitch of the bf16 terms, 16-byte output pieces
@@ -682,10 +736,11 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
       return MVD_ERR_UNSUPPORTED;
   }
   {
-    const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, 3};
+    const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)terms};
     const cuuint64_t gstr[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
     const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBN, 1u};
-    if (enc(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_terms), gdim, gstr, box, estr,
+    if (enc(&tm_b, terms == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+            const_cast<void*>(w_terms), gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MVD_ERR_UNSUPPORTED;
@@ -701,9 +756,10 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
   prm.n_tiles = (int)ceil_div64(N, kBN);
   prm.multicast = multicast;
   if (ts) {  // persistent over row blocks; the column tiles of a row block run back to back on one SM
-    MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem));
+    auto kern = terms == 3 ? linear_split_ts_kernel<3> : linear_split_ts_kernel<2>;
+    MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem));
     const unsigned grid = (unsigned)(prm.m_blocks < kNumSMs ? prm.m_blocks : kNumSMs);
-    linear_bf16x3_ts_kernel<<<grid, kTsThreads, kTsSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+    kern<<<grid, kTsThreads, kTsSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
   } else {
     MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
     const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;
@@ -719,7 +775,7 @@ extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const 
   return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out, 0, 0, stream);
 }
 
-// Same arithmetic (bit-identical results), x terms staged in tensor memory: see linear_bf16x3_ts_kernel.
+// Same arithmetic (bit-identical results), x terms staged in tensor memory: see linear_split_ts_kernel<3>.
 extern "C" int mvd_linear_bf16x3_ts_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
                                         int relu, float* out, void* stream) {
   return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out, 0, 1, stream);
@@ -732,6 +788,17 @@ extern "C" int mvd_linear_bf16x3_ts_f32(const float* x, const void* w_terms, con
 extern "C" int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
                                                int N, int relu, float* out_mc, void* stream) {
   return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out_mc, 1, 0, stream);
+}
+
+// Two fp16 terms, three products (see linear_split_ts_kernel<2>): w_terms [2][N][K] fp16 from mvd_f16_split2_f32.
+extern "C" int mvd_linear_f16x2_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
+                                    int relu, float* out, void* stream) {
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out, 0, 1, stream, 2);
+}
+
+extern "C" int mvd_linear_f16x2_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
+                                              int N, int relu, float* out_mc, void* stream) {
+  return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out_mc, 1, 1, stream, 2);
 }
 
 extern "C" int mvd_linear_bf16x3_ts_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows,

@@ -34,7 +34,7 @@ struct VgParams {
   const float* logit_bias;  // FUSED, nullable: [M, L, P]
   int H, W, M, L, R;
   int TH, TW, tiles_x;
-  int BW, BH;                                 // window = tile + 2*halo
+  int BW, BH, halo;                           // window = tile + 2*halo
   uint32_t off_a, off_b, off_ref;             // byte offsets of the per-stage regions (window is at 0)
   uint32_t stage_bytes, zero_off, zero_bytes; // stage pitch; zero pad region (after both stages)
   uint32_t tx_bytes;                          // bytes landing per stage
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
   const int tile = blockIdx.x;
   const int ty0 = (tile / prm.tiles_x) * prm.TH, tx0 = (tile % prm.tiles_x) * prm.TW;
   const int m = blockIdx.y, b = blockIdx.z;
-  const int wy0 = ty0 - kHalo, wx0 = tx0 - kHalo;  // window origin in level pixels (may be negative: TMA zero fill)
+  const int wy0 = ty0 - prm.halo, wx0 = tx0 - prm.halo;  // window origin in level pixels (may be negative: TMA zero fill)
 
   auto issue_level = [&](int lv) {  // one lane: everything level `lv` needs -> stage lv & 1
     const uint32_t st = smem0 + (uint32_t)(lv & 1) * prm.stage_bytes, bar = bar_full + 8u * (uint32_t)(lv & 1);
@@ -311,7 +311,7 @@ int viewgrid_dispatch(const float* value, const float* loc, const float* attn, c
                        reinterpret_cast<uintptr_t>(ref);
   if (al & 15u) return MVD_ERR_MISALIGNED;
   VgPlan pl;
-  if (!plan_viewgrid(D, R, P, FUSED, &pl)) return MVD_ERR_UNSUPPORTED;
+  if (!plan_viewgrid(D, R, P, FUSED, &pl, viewgrid_halo(P))) return MVD_ERR_UNSUPPORTED;
   pl.tiles_x = (W + pl.TW - 1) / pl.TW;
   pl.tiles_y = (H + pl.TH - 1) / pl.TH;
 
@@ -362,6 +362,7 @@ int viewgrid_dispatch(const float* value, const float* loc, const float* attn, c
   prm.tiles_x = pl.tiles_x;
   prm.BW = pl.BW;
   prm.BH = pl.BH;
+  prm.halo = pl.halo;
   prm.off_a = pl.off_a;
   prm.off_b = pl.off_b;
   prm.off_ref = pl.off_ref;

@@ -10,7 +10,10 @@
 namespace mvd {
 namespace {
 
-constexpr int kHalo = 6;          // pixels around the tile kept in the window (default init samples +-4 px: ms_deform_attn.py:62-77)
+constexpr int kHalo = 6;          // pixels around the tile kept in the window (default init samples +-P px, P = 4: ms_deform_attn.py:62-77)
+// P > 4: the default pattern reaches +-P px, whose 2x2 footprints need P + 1 (r02i: the 8-point stress shape ran at 0.06 of
+// the roofline with a quarter of its samples on the masked global path)
+inline int viewgrid_halo(int P) { return P <= 4 ? kHalo : P + 1; }
 constexpr int kMaxThreads = 448;  // 2 blocks/SM at <= 72 registers
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -108,36 +111,41 @@ __device__ __forceinline__ void read_record(const unsigned char* base, int idx, 
 }
 
 struct VgPlan {
-  int TH, TW, BW, BH, tiles_x, tiles_y, threads;
+  int TH, TW, BW, BH, halo, tiles_x, tiles_y, threads;
   uint32_t off_a, off_b, off_ref, stage_bytes, zero_off, zero_bytes, tx_bytes;
   size_t smem;
 };
 
 inline uint32_t up128(size_t v) { return (uint32_t)((v + 127) & ~(size_t)127); }
 
-// Tile = TH x TW ground cells with TH*TW*R <= kMaxThreads threads; prefers 64 cells (4x16), 32 (4x8) for many views.
-bool plan_viewgrid(int D, int R, int P, bool fused, VgPlan* pl) {
+// Tile = TH x TW ground cells with TH*TW*R <= kMaxThreads threads; prefers 64 cells (4x16), 32 (4x8) for many views; the
+// tile is narrowed further while two stages of window + records do not fit the shared memory of one block.
+bool plan_viewgrid(int D, int R, int P, bool fused, VgPlan* pl, int halo = kHalo) {
   int TH = 4, TW = 16;
   while (TH * TW * R > kMaxThreads && TW > 4) TW >>= 1;
   while (TH * TW * R > kMaxThreads && TH > 1) TH >>= 1;
   if (TH * TW * R > kMaxThreads || R > 256) return false;
-  pl->TH = TH;
-  pl->TW = TW;
-  pl->BW = TW + 2 * kHalo;
-  pl->BH = TH + 2 * kHalo;
-  pl->threads = ((TH * TW * R + 31) / 32) * 32;
-  const size_t nbox = (size_t)TH * TW * R;
-  const size_t win = (size_t)pl->BW * pl->BH * D * 4, a = nbox * 2 * P * 4, b = nbox * P * 4,
-               rf = fused ? (size_t)TH * TW * 2 * P * 4 : 0;
-  pl->off_a = up128(win);
-  pl->off_b = pl->off_a + up128(a);
-  pl->off_ref = pl->off_b + up128(b);
-  pl->stage_bytes = pl->off_ref + up128(rf);
-  pl->tx_bytes = (uint32_t)(win + a + b + rf);
-  pl->zero_off = 2 * pl->stage_bytes;
-  pl->zero_bytes = up128((size_t)pl->BW * D * 4 + 2 * D * 4);  // reach of a 2x2 footprint from its top-left pixel
-  pl->smem = (size_t)pl->zero_off + pl->zero_bytes;
-  return pl->smem <= 227 * 1024 && 2 * P * TW <= 256;
+  for (;; TW >>= 1) {
+    pl->TH = TH;
+    pl->TW = TW;
+    pl->halo = halo;
+    pl->BW = TW + 2 * halo;
+    pl->BH = TH + 2 * halo;
+    pl->threads = ((TH * TW * R + 31) / 32) * 32;
+    const size_t nbox = (size_t)TH * TW * R;
+    const size_t win = (size_t)pl->BW * pl->BH * D * 4, a = nbox * 2 * P * 4, b = nbox * P * 4,
+                 rf = fused ? (size_t)TH * TW * 2 * P * 4 : 0;
+    pl->off_a = up128(win);
+    pl->off_b = pl->off_a + up128(a);
+    pl->off_ref = pl->off_b + up128(b);
+    pl->stage_bytes = pl->off_ref + up128(rf);
+    pl->tx_bytes = (uint32_t)(win + a + b + rf);
+    pl->zero_off = 2 * pl->stage_bytes;
+    pl->zero_bytes = up128((size_t)pl->BW * D * 4 + 2 * D * 4);  // reach of a 2x2 footprint from its top-left pixel
+    pl->smem = (size_t)pl->zero_off + pl->zero_bytes;
+    if (pl->smem <= 227 * 1024 && 2 * P * TW <= 256) return true;
+    if (TW <= 4) return false;
+  }
 }
 
 int encode(CUtensorMap* map, const float* base, int rank, const cuuint64_t* gdim, const cuuint64_t* gstr,

@@ -422,6 +422,7 @@ _GEMM_TS = os.environ.get("MVDETR_B200_GEMM_TS", "0") == "1"
 _gemm_ws = {}
 _tf32_split_cache = _TensorCache()
 _bf16_split_cache = _TensorCache()
+_f16_split_cache = _TensorCache()
 
 
 def _bf16_split3(weight):
@@ -435,6 +436,19 @@ def _bf16_split3(weight):
             rc = _C.lib.mvd_bf16_split3_f32(w.data_ptr(), w.numel(), terms.data_ptr(), _stream(w))
         _C.check(rc, "mvd_bf16_split3_f32")
         got = _bf16_split_cache.put(weight, terms)
+    return got
+
+
+def _f16_split2(weight):
+    """[2, N, K] fp16 terms of an fp32 weight (t0 = fp16(w), t1 = fp16((w - t0) * 2^11)), once per weight object and version."""
+    got = _f16_split_cache.get(weight)
+    if got is None:
+        w = weight.detach()
+        terms = torch.empty((2, *w.shape), dtype=torch.float16, device=w.device)
+        with _on_device(w):
+            rc = _C.lib.mvd_f16_split2_f32(w.data_ptr(), w.numel(), terms.data_ptr(), _stream(w))
+        _C.check(rc, "mvd_f16_split2_f32")
+        got = _f16_split_cache.put(weight, terms)
     return got
 
 
@@ -468,7 +482,7 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
     rows, K = x.shape
     N = weight.shape[0]
     x = x.contiguous()
-    if mode in ("tf32x3", "bf16x3", "bf16x3ts", "bf16x3ss"):
+    if mode in ("tf32x3", "bf16x3", "bf16x3ts", "bf16x3ss", "f16x2"):
         for name, t in (("x", x), ("weight", weight), ("bias", bias)):
             if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
                 raise RuntimeError(f"linear: {name} must be a contiguous fp32 CUDA tensor")
@@ -477,6 +491,13 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
         elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (rows, N)):
             raise RuntimeError("linear: out must be a contiguous fp32 CUDA tensor [rows, N]")
         bp = bias.data_ptr() if bias is not None else None
+        if mode == "f16x2" and K % 8 == 0:
+            terms = _f16_split2(weight)
+            with _on_device(x):
+                rc = _C.lib.mvd_linear_f16x2_f32(x.data_ptr(), terms.data_ptr(), bp, rows, K, N, 1 if relu else 0,
+                                                 out.data_ptr(), _stream(x))
+            _C.check(rc, "mvd_linear_f16x2_f32")
+            return out
         if mode != "tf32x3" and K % 8 == 0:
             terms = _bf16_split3(weight)
             ts = mode == "bf16x3ts" or (mode == "bf16x3" and _GEMM_TS)   # "bf16x3ss": shared-memory operands explicitly
@@ -535,8 +556,11 @@ def linear_multicast(x, weight, bias, mc_ptr, relu=False):
     for name, t in (("x", x), ("weight", weight), ("bias", bias)):
         if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
             raise RuntimeError(f"linear_multicast: {name} must be a contiguous fp32 CUDA tensor")
-    terms = _bf16_split3(weight)
-    fn = _C.lib.mvd_linear_bf16x3_ts_multicast_f32 if _GEMM_TS else _C.lib.mvd_linear_bf16x3_multicast_f32
+    if _GEMM_MODE == "f16x2":
+        terms, fn = _f16_split2(weight), _C.lib.mvd_linear_f16x2_multicast_f32
+    else:
+        terms = _bf16_split3(weight)
+        fn = _C.lib.mvd_linear_bf16x3_ts_multicast_f32 if _GEMM_TS else _C.lib.mvd_linear_bf16x3_multicast_f32
     with _on_device(x):
         rc = fn(x.data_ptr(), terms.data_ptr(), bias.data_ptr() if bias is not None else None, rows, K, N,
                 1 if relu else 0, int(mc_ptr), _stream(x))
@@ -566,6 +590,9 @@ def gemm_mode_text():
         return ("bf16x3: own persistent tcgen05.mma.kind::f16 kernel (3-term bf16 split in-kernel, 6 products, fp32 "
                 "accumulate in TMEM, bias/ReLU epilogue, TMA rings; x terms in "
                 + ("tensor memory (TS-form MMA)" if _GEMM_TS else "shared memory") + "), fp32-level accuracy")
+    if _GEMM_MODE == "f16x2":
+        return ("f16x2: own persistent tcgen05.mma.kind::f16 kernel (2-term fp16 split in-kernel, second term scaled by "
+                "2^11, 3 products, fp32 accumulate in TMEM, x terms in tensor memory), fp32-level accuracy for |x|,|w| < 65504")
     if _GEMM_MODE == "tf32x3":
         return ("tf32x3: own tcgen05.mma.kind::tf32 kernel (3xTF32 split in-kernel, fp32 accumulate in TMEM, bias/ReLU "
                 "epilogue), fp32-level accuracy")

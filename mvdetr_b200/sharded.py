@@ -133,7 +133,7 @@ class ShardedFusion:
         """True when the all-gathers run as multicast stores from our kernels' epilogues instead of ncclAllGather."""
         if self.symm is None:
             self.symm = SymmetricBuffers(device, self.group) if (self.world > 1 and device.type == "cuda" and
-                                                                 ops._GEMM_MODE == "bf16x3") else False
+                                                                 ops._GEMM_MODE in ("bf16x3", "f16x2")) else False
         return bool(self.symm) and self.symm.available
 
     def _buf(self, key, shape, like):

@@ -47,7 +47,7 @@ def main():
             exact = exact.clamp_min(0)
         rec = {"name": name, "rows": rows, "K": K, "N": N, "relu": relu,
                "hbm_floor_us": 4 * (rows * K + rows * N + N * K) / 6549.8e3}
-        for mode in ("bf16x3ss", "bf16x3ts", "tf32x3", "bf16x9", "torch"):
+        for mode in ("f16x2", "bf16x3ts", "bf16x3ss", "tf32x3", "bf16x9", "torch"):
             try:
                 out = ops.linear(x, w, b, relu=relu, mode=mode)
                 rec[mode + "_err"] = (out[:4096].double() - exact).abs().max().item()

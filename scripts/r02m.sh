@@ -5,24 +5,9 @@ set -u
 TAG="${1:-r02m}"
 OUT=gpurun_out
 mkdir -p $OUT
-cat > /tmp/ts_check.py <<'PY'
-import torch
-from mvdetr_b200 import ops
-dev = torch.device("cuda:0")
-g = torch.Generator().manual_seed(0)
-ok = True
-for rows, K, N in [(300, 128, 448), (129, 64, 128), (1000, 512, 128), (257, 288, 256), (5, 8, 4), (75600, 128, 512)]:
-    x = torch.randn(rows, K, generator=g).to(dev); w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev); b = torch.randn(N, generator=g).to(dev)
-    a = ops.linear(x, w, b, mode="bf16x3ts"); s = ops.linear(x, w, b, mode="bf16x3ss")
-    torch.cuda.synchronize()
-    e = (a.double() - (x.double() @ w.double().t() + b.double())).abs().max().item()
-    print(rows, K, N, "err", e, "equal_to_ss", torch.equal(a, s), "max diff to ss", (a - s).abs().max().item(), flush=True)
-    ok = ok and e < 1e-4
-raise SystemExit(0 if ok else 1)
-PY
-echo "== quick check (TS kernel)"; timeout -s KILL 150 python /tmp/ts_check.py 2>&1 | tail -12; RC=${PIPESTATUS[0]}; echo "quick rc=$RC"
+echo "== quick check (TS kernel)"; timeout -s KILL 150 python scripts/ts_check.py 2>&1 | tail -12; RC=${PIPESTATUS[0]}; echo "quick rc=$RC"
 if [ "$RC" != "0" ]; then
-  echo "== sanitizer (TS kernel, small shapes)"; timeout -s KILL 300 compute-sanitizer --tool memcheck python /tmp/ts_check.py > $OUT/${TAG}_sanitizer_ts.log 2>&1
+  echo "== sanitizer (TS kernel, small shapes)"; timeout -s KILL 300 compute-sanitizer --tool memcheck python scripts/ts_check.py > $OUT/${TAG}_sanitizer_ts.log 2>&1
   echo "sanitizer rc=$?"; grep -E "err|ERROR SUMMARY|Invalid|Error|at 0x|by thread" $OUT/${TAG}_sanitizer_ts.log | head -30
   exit 1
 fi
@@ -37,3 +22,15 @@ echo "== bench ours TS=$TS" ; MVDETR_B200_GEMM_TS=$TS timeout -s KILL 600 python
 done
 echo "== fullsize parity with TS"; MVDETR_B200_GEMM_TS=1 timeout -s KILL 600 python -m pytest tests/test_fullsize_gpu.py tests/test_world_feat_gpu.py -m gpu -q --timeout 300 2>&1 | tail -4
 echo "== timeline TS"; MVDETR_B200_GEMM_TS=1 timeout -s KILL 300 python scripts/timeline.py --out $OUT/${TAG}_timeline_ts > /dev/null 2> $OUT/${TAG}_timeline.err; echo "rc=$?"; head -14 $OUT/${TAG}_timeline_ts.txt | cut -c1-150
+echo "== msda tests (halo by P)"; timeout -s KILL 600 python -m pytest tests/test_msda_gpu.py tests/test_fullsize_gpu.py -m gpu -q --timeout 300 2>&1 | tail -4
+echo "== bench stress4k"; MVDETR_B200_GEMM_TS=1 timeout -s KILL 900 python bench.py --workload stress4k --steps 10 --warmup 3 > $OUT/${TAG}_bench_stress4k.json 2> $OUT/${TAG}_bench_stress4k.err; echo "rc=$?"; cut -c1-200 $OUT/${TAG}_bench_stress4k.json; tail -2 $OUT/${TAG}_bench_stress4k.err
+python - <<PY
+import json,glob
+for f in sorted(glob.glob('gpurun_out/${TAG}_bench*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception as e:
+        print(f,'unparsable',e); continue
+    print(f, 'value',round(d.get('value',0),2),'ms',round(d.get('ms_per_step',0),3),'e2e',round(d.get('e2e',{}).get('value',0),2), 'launches', d.get('gpu_launches'), 'roofline', round(d.get('roofline',{}).get('frac',0),3), 'msda us', round(d.get('roofline',{}).get('us_per_launch',0),1))
+    if 'ref_cuda_frame' in d: print('    ref_cuda_frame diff', d['ref_cuda_frame'].get('max_abs_diff_vs_ours'))
+PY

@@ -43,7 +43,7 @@ def test_frame_runner_full_size_vs_cpu_oracle(cuda, scene):
     hidden, heads, points = 128, 8, 4
     ds, fusion = _fusion(scene, hidden, heads, points, cuda)
     # the configuration bench.py reports: convolutions as im2col GEMMs, dense layers on our tcgen05 kernel (or cuBLASLt)
-    assert fusion.gemm_path and (ops._GEMM_MODE in ("bf16x3", "tf32x3") or ops.linear_available() >= 120900)
+    assert fusion.gemm_path and (ops._GEMM_MODE in ("bf16x3", "f16x2", "tf32x3") or ops.linear_available() >= 120900)
     N, (Hg, Wg) = ds.num_cam, ds.Rworld_shape
     g = torch.Generator().manual_seed(3)
     feat = torch.randn(N, hidden, *ds.Rimg_shape, generator=g)

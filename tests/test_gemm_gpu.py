@@ -44,7 +44,7 @@ def test_linear_torch_mode_needs_no_library(cuda):
 @pytest.mark.parametrize("rows,K,N", [(75600, 128, 128), (4099, 128, 448), (2048, 128, 224), (3000, 128, 512),
                                       (3000, 512, 128), (1000, 1152, 128), (77, 896, 128), (130, 36, 20), (1, 4, 4),
                                       (129, 2304, 256), (20000, 128, 128), (641, 40, 132)])
-@pytest.mark.parametrize("mode", ["bf16x3ss", "bf16x3ts", "tf32x3"])
+@pytest.mark.parametrize("mode", ["bf16x3ss", "bf16x3ts", "f16x2", "tf32x3"])
 def test_own_tensor_core_kernels_are_fp32_accurate(cuda, rows, K, N, mode):
     """Our tcgen05 kernels (operands split into bf16 / tf32 terms, accumulators in tensor memory) against an fp64 product:
     bf16x3 (six products) must be as accurate as the native fp32 GEMM, the 3xTF32 variant within a small multiple of it;
@@ -82,7 +82,7 @@ def test_split_cache_is_keyed_on_the_tensor_object(cuda):
     x = torch.randn(256, 64, generator=g).to(cuda)
     for i in range(4):
         w = torch.randn(64, 64, generator=g).to(cuda)   # same shape: the allocator reuses the block just freed
-        for mode in ("bf16x3", "tf32x3"):
+        for mode in ("bf16x3", "f16x2", "tf32x3"):
             got = ops.linear(x, w, None, mode=mode)
             assert (got.double() - x.double() @ w.double().t()).abs().max().item() <= 1e-4, (i, mode)
         del w
