@@ -359,17 +359,27 @@ __global__ void __launch_bounds__(kBThreads, 1)
 //   (one accumulator buffer: the 8 epilogue warps first drain it into registers and hand it back, then do bias / ReLU /
 //   stores under the next tile's main loop)
 //   warps: 0 TMA, 1 MMA, 2-5 split (TMEM lane quarter = warp & 3), 6-13 epilogue (quarter = warp & 3, column half)
-constexpr int kTsThreads = 448;
-constexpr int kTsRawStages = 4, kTsWStages = 4, kTsAStages = 4;
-constexpr int kTsOffRaw = 0;
-constexpr int kTsOffW = kTsOffRaw + kTsRawStages * kRawBytes;            //  64 KB
-constexpr int kTsOffStage = kTsOffW + kTsWStages * 3 * kHalfBytes;       // +96 KB
-constexpr int kTsSmemUsed = kTsOffStage + 8 * 32 * kStagePitch * 4;      // +36 KB = 196 KB
-constexpr int kTsSmem = kTsSmemUsed + 1024;
+constexpr int kTsThreads = 480;  // warps: 0 x-tile TMA, 1 MMA, 2-5 split, 6-13 epilogue, 14 weight-term TMA
 constexpr uint32_t kTsAccCols = 2 * kBN;      // leading + small-terms accumulators
-constexpr uint32_t kTsAStageCols = 48;        // 3 terms x 16 columns (32 bf16 of K per lane)
-constexpr uint32_t kTsTmemCols = 512;         // 256 + 4 x 48 = 448, rounded to a power of two
-constexpr int kTsNumBars = 2 * kTsRawStages + 2 * kTsWStages + 2 * kTsAStages + 2;
+constexpr uint32_t kTsTmemCols = 512;
+// r02n: with the x and W loads issued by ONE thread the W ring (4 stages) capped the x prefetch at 4 tiles = 64 KB per SM,
+// 9.5 MB in flight on the chip, and the big-K layers ran at half the HBM rate (0.68 us per chunk). The two streams now have
+// their own producer warps and the x ring takes all the shared memory that is left.
+template <int NT>
+struct TsCfg {
+  static constexpr int kRaw = NT == 2 ? 8 : 7;               // fp32 x tiles in flight (16 KB each)
+  static constexpr int kW = 3;                               // weight-term stages (L2-resident source)
+  static constexpr int kA = NT == 2 ? 8 : 5;                 // x-term stages in tensor memory
+  static constexpr uint32_t kAStageCols = NT * 16;           // NT terms x 16 columns (32 k of one row per lane)
+  static constexpr int kWBytes = NT * kHalfBytes;
+  static constexpr int kOffRaw = 0;
+  static constexpr int kOffW = kOffRaw + kRaw * kRawBytes;
+  static constexpr int kOffStage = kOffW + kW * kWBytes;
+  static constexpr int kSmem = kOffStage + 8 * 32 * kStagePitch * 4 + 1024;  // NT=2: 213 KB, NT=3: 221 KB
+  static constexpr int kNumBars = 2 * kRaw + 2 * kW + 2 * kA + 2;
+  static_assert(kTsAccCols + kA * kAStageCols <= kTsTmemCols, "tensor memory");
+  static_assert(kSmem <= 227 * 1024, "shared memory");
+};
 
 // fp16 operands (format 0) instead of bf16 (format 1): the two-term variant below
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
@@ -424,8 +434,12 @@ __global__ void __launch_bounds__(kTsThreads, 1)
     linear_split_ts_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                            const GbParams prm) {
   constexpr uint32_t IDESC = NT == 3 ? kIdescBf16 : kIdescF16;
+  using Cfg = TsCfg<NT>;
+  constexpr int kTsRawStages = Cfg::kRaw, kTsWStages = Cfg::kW, kTsAStages = Cfg::kA;
+  constexpr uint32_t kTsAStageCols = Cfg::kAStageCols;
+  constexpr int kTsOffRaw = Cfg::kOffRaw, kTsOffW = Cfg::kOffW, kTsOffStage = Cfg::kOffStage, kWBytes = Cfg::kWBytes;
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) unsigned long long s_bar[kTsNumBars];
+  __shared__ __align__(8) unsigned long long s_bar[TsCfg<NT>::kNumBars];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(16) float s_bias[kBN];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -476,27 +490,34 @@ __global__ void __launch_bounds__(kTsThreads, 1)
   const int a_loads = reuse ? nk : prm.n_tiles * nk;  // x chunks loaded and split per row block
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer ------------------------------------------------
+    // ------------------------------------------------ TMA producer: fp32 x tiles -----------------------------------
     if (lane == 0) {
-      uint32_t ia = 0, iw = 0;
+      uint32_t ia = 0;
       for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
         const int m0 = mb * kBM;
+        for (int l = 0; l < a_loads; ++l, ++ia) {
+          const int kc = l % nk;
+          const uint32_t rs = ia % kTsRawStages;
+          mbar_wait(b_raw_empty + 8u * rs, ((ia / kTsRawStages) & 1u) ^ 1u);  // first lap: passes at once
+          mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
+          tma_load_2d_b(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
+        }
+      }
+    }
+  } else if (warp == 14) {
+    // ------------------------------------------------ TMA producer: weight terms (one chunk per column tile and k) --
+    if (lane == 0) {
+      uint32_t iw = 0;
+      for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
         for (int nt = 0; nt < prm.n_tiles; ++nt) {
           const int n0 = nt * kBN;
           for (int kc = 0; kc < nk; ++kc, ++iw) {
-            if (!reuse || nt == 0) {
-              const uint32_t rs = ia % kTsRawStages;
-              mbar_wait(b_raw_empty + 8u * rs, ((ia / kTsRawStages) & 1u) ^ 1u);  // first lap: passes at once
-              mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
-              tma_load_2d_b(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
-              ++ia;
-            }
             const uint32_t ws = iw % kTsWStages;
             mbar_wait(b_w_empty + 8u * ws, ((iw / kTsWStages) & 1u) ^ 1u);
-            mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)(NT * kHalfBytes));
+            mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)kWBytes);
 #pragma unroll
             for (int i = 0; i < NT; ++i)
-              tma_load_3d(base + kTsOffW + (ws * 3 + i) * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
+              tma_load_3d(base + kTsOffW + ws * kWBytes + i * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
           }
         }
       }
@@ -516,7 +537,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
             if (!reuse || nt == 0) mbar_wait(b_a_full + 8u * as, (a_idx / kTsAStages) & 1u);  // x terms stored by 128 threads
             mbar_wait(b_w_full + 8u * ws, (iw / kTsWStages) & 1u);                              // weight terms landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = tmem + kTsAccCols + as * kTsAStageCols, b0 = base + kTsOffW + ws * 3 * kHalfBytes;
+            const uint32_t a0 = tmem + kTsAccCols + as * kTsAStageCols, b0 = base + kTsOffW + ws * kWBytes;
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {  // UMMA K = 16 bf16: 8 tensor-memory columns of A, 32 bytes of a W row
               uint32_t ta[NT];
@@ -586,7 +607,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         mbar_arrive(b_a_full + 8u * as);
       }
     }
-  } else {
+  } else if (warp < 14) {
     // ------------------------------------------------ epilogue (warps 6-13) ---------------------------------------
     const int q = warp & 3, half = (warp - 6) >> 2;  // tensor-memory lane quarter, 64-column half of the tile
     const int et = tid - 192;
@@ -757,9 +778,10 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
   prm.multicast = multicast;
   if (ts) {  // persistent over row blocks; the column tiles of a row block run back to back on one SM
     auto kern = terms == 3 ? linear_split_ts_kernel<3> : linear_split_ts_kernel<2>;
-    MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem));
+    const int smem = terms == 3 ? TsCfg<3>::kSmem : TsCfg<2>::kSmem;
+    MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned grid = (unsigned)(prm.m_blocks < kNumSMs ? prm.m_blocks : kNumSMs);
-    kern<<<grid, kTsThreads, kTsSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+    kern<<<grid, kTsThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
   } else {
     MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
     const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;

@@ -207,7 +207,11 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
         w2[i] = in ? hh * lw * a : 0.f;
         w3[i] = in ? lh * hw * a : 0.f;
         w4[i] = in ? lh * lw * a : 0.f;
-        off[i] = in ? (dy * BW + dx) * PX_BYTES : zoff;
+        // zero-pad reads keep the bank group of the lane's would-be window address (same offset mod 128): r02i ncu source
+        // page: every corner load carried ~12 % excess wavefronts, the border warps whose out-of-level lanes all hit ONE
+        // zero-pad address and collided with a neighbour's window read
+        const int nat = (dy * BW + dx) * PX_BYTES;
+        off[i] = in ? nat : zoff + (nat & 127);
         far |= (unsigned)(v && !in) << i;
       }
       // ---- window path, branch-free: far samples were given zero weights on the zero pad ----

@@ -141,7 +141,7 @@ bool plan_viewgrid(int D, int R, int P, bool fused, VgPlan* pl, int halo = kHalo
     pl->stage_bytes = pl->off_ref + up128(rf);
     pl->tx_bytes = (uint32_t)(win + a + b + rf);
     pl->zero_off = 2 * pl->stage_bytes;
-    pl->zero_bytes = up128((size_t)pl->BW * D * 4 + 2 * D * 4);  // reach of a 2x2 footprint from its top-left pixel
+    pl->zero_bytes = up128((size_t)pl->BW * D * 4 + 2 * D * 4) + 128;  // reach of a 2x2 footprint from its top-left pixel (+ bank-preserving start offset < 128)
     pl->smem = (size_t)pl->zero_off + pl->zero_bytes;
     if (pl->smem <= 227 * 1024 && 2 * P * TW <= 256) return true;
     if (TW <= 4) return false;

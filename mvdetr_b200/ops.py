@@ -416,9 +416,9 @@ def _as_nhwc(x):
 
 
 # "bf16x3" / "tf32x3": OUR tcgen05 kernels (split operands, fp32-level accuracy) | "bf16x9" / "fp32": cuBLASLt 12.9 | "torch"
-_GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "bf16x3")
+_GEMM_MODE = os.environ.get("MVDETR_B200_GEMM", "f16x2")
 # bf16x3 only: x terms staged in tensor memory (tcgen05.mma with A from TMEM) instead of shared memory; same results
-_GEMM_TS = os.environ.get("MVDETR_B200_GEMM_TS", "0") == "1"
+_GEMM_TS = os.environ.get("MVDETR_B200_GEMM_TS", "1") == "1"
 _gemm_ws = {}
 _tf32_split_cache = _TensorCache()
 _bf16_split_cache = _TensorCache()

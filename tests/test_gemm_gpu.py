@@ -58,7 +58,10 @@ def test_own_tensor_core_kernels_are_fp32_accurate(cuda, rows, K, N, mode):
     # 3xTF32 (one accumulator, 3 roundings of the accumulator per k-step): a few 1e-6 relative, growing with K --
     # inside the 1e-4 bar; ops.linear only uses it when K % 8 != 0.
     scale = exact.abs().max().item()
-    tol = max(2.5 * err_torch, 2e-6 * scale) if mode != "tf32x3" else max(8 * err_torch, 1.5e-5 * scale)
+    # f16x2 (two fp16 terms, three products): fp16 products carry 22 significant bits, of which the tensor core's adder drops
+    # the lowest when it aligns them to the accumulator: measured 1.0-1.4x the native fp32 GEMM's error (r02n).
+    tol = {"tf32x3": max(8 * err_torch, 1.5e-5 * scale), "f16x2": max(4 * err_torch, 4e-6 * scale)}.get(
+        mode, max(2.5 * err_torch, 2e-6 * scale))
     got = ops.linear(x, w, b, mode=mode)
     assert (got.double() - exact).abs().max().item() <= tol
     if mode == "bf16x3ts":  # x terms in tensor memory: same products, same order, same accumulators as the shared-memory kernel
