@@ -441,7 +441,6 @@ __global__ void __launch_bounds__(kTsThreads, 1)
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long s_bar[TsCfg<NT>::kNumBars];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(16) float s_bias[kBN];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -609,15 +608,27 @@ __global__ void __launch_bounds__(kTsThreads, 1)
     }
   } else if (warp < 14) {
     // ------------------------------------------------ epilogue (warps 6-13) ---------------------------------------
+    // r02o (ncu source page): the MMA warp spent its time waiting for the accumulator to be handed back -- the epilogue
+    // was the bottleneck at 3.5 us per 128 x 128 tile: a bias tile reloaded from global memory into shared memory
+    // behind two 256-thread barriers per tile, and load -> add -> store chains serialised on one register quad. Now each
+    // lane fetches the two 16-byte bias pieces of ITS columns before it waits for the accumulator, the raw sums go
+    // through the transposition stage, and bias / ReLU are applied on the way out (8 independent loads, then 8 stores).
     const int q = warp & 3, half = (warp - 6) >> 2;  // tensor-memory lane quarter, 64-column half of the tile
-    const int et = tid - 192;
     float* stg = reinterpret_cast<float*>(sm + kTsOffStage) + (size_t)(warp - 6) * 32 * kStagePitch;
     const uint32_t t_hi = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64), t_lo = t_hi + (uint32_t)kBN;
+    const int piece = lane & 7;
     uint32_t tcount = 0;
     for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
       const int r0 = mb * kBM + q * 32;
       for (int nt = 0; nt < prm.n_tiles; ++nt, ++tcount) {
-        const int n0 = nt * kBN;
+        const int n0 = nt * kBN + half * 64 + piece * 4;  // first column of this lane's piece in column block 0
+        float4 bb[2];
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const int n = n0 + cb * 32;
+          bb[cb] = (prm.bias && n < prm.N) ? __ldg(reinterpret_cast<const float4*>(prm.bias + n))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         mbar_wait(b_acc_full, tcount & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float o[64];  // own row, own 64 columns: sum of the two accumulators
@@ -634,40 +645,35 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(b_acc_empty);  // accumulator handed back: the next tile's MMAs run under the rest of this epilogue
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with s_bias
-        if (et < kBN) {
-          const int n = n0 + et;
-          s_bias[et] = (prm.bias && n < prm.N) ? __ldg(prm.bias + n) : 0.f;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
         for (int cb = 0; cb < 2; ++cb) {  // 32 x 32 sub-tiles through the warp's stage: full 128-byte row segments
-          const int c = half * 64 + cb * 32;
           __syncwarp();  // the previous sub-tile's readers are done with the stage
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(s_bias + c + j);
-            float4 x;
-            x.x = o[cb * 32 + j] + bb.x;
-            x.y = o[cb * 32 + j + 1] + bb.y;
-            x.z = o[cb * 32 + j + 2] + bb.z;
-            x.w = o[cb * 32 + j + 3] + bb.w;
-            if (prm.relu) {
-              x.x = fmaxf(x.x, 0.f);
-              x.y = fmaxf(x.y, 0.f);
-              x.z = fmaxf(x.z, 0.f);
-              x.w = fmaxf(x.w, 0.f);
-            }
-            *reinterpret_cast<float4*>(stg + lane * kStagePitch + j) = x;
-          }
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * kStagePitch + j) =
+                make_float4(o[cb * 32 + j], o[cb * 32 + j + 1], o[cb * 32 + j + 2], o[cb * 32 + j + 3]);
           __syncwarp();
-          const int piece = lane & 7, n = n0 + c + piece * 4;
-          if (n < prm.N) {
+          const int n = n0 + cb * 32;
+          if (n < prm.N) {  // N % 4 == 0: a 4-column piece is inside or outside as a whole
+            float4 xs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              xs[i] = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * i) * kStagePitch + piece * 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = (lane >> 3) + 4 * i;
+              float4 x = xs[i];
+              x.x += bb[cb].x;
+              x.y += bb[cb].y;
+              x.z += bb[cb].z;
+              x.w += bb[cb].w;
+              if (prm.relu) {
+                x.x = fmaxf(x.x, 0.f);
+                x.y = fmaxf(x.y, 0.f);
+                x.z = fmaxf(x.z, 0.f);
+                x.w = fmaxf(x.w, 0.f);
+              }
               if (r0 + rr < prm.rows) {
-                const float4 x = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + piece * 4);
                 float* dst = prm.out + (int64_t)(r0 + rr) * prm.N + n;
                 if (prm.multicast)
                   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x),

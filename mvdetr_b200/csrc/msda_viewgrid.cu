@@ -41,13 +41,18 @@ struct VgParams {
 };
 
 // Blocks per SM: the D=16/P=4 stage (51 KB) fits twice; larger head dims or point counts are limited to one block by
-// shared memory anyway, so they get the whole register file (no spills for the 32 accumulators of D=32).
-template <int D, int P, bool FUSED>
-__global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
+// shared memory anyway, so they get the whole register file.
+// SPLIT = 2 (D = 32): two ADJACENT lanes share a (query, head) pair and own 16 channels each. r02i: with one thread per
+// pair the D=32 / P=8 stress shape ran 256 threads = 8 warps per SM with 32 accumulators each and sat at 0.06 of the
+// roofline, bound by shared-memory latency; the split doubles the warps per window and halves the registers per thread.
+// Both lanes of a pair repeat the sample arithmetic (identical values) and read the same records (broadcast).
+constexpr int kMaxThreadsSplit = 512;
+template <int D, int P, bool FUSED, int SPLIT>
+__global__ void __launch_bounds__(SPLIT == 2 ? kMaxThreadsSplit : kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
     msda_vg_kernel(const __grid_constant__ CUtensorMap tm_val, const __grid_constant__ CUtensorMap tm_a,
                    const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_ref,
                    const VgParams prm) {
-  constexpr int NQ = D / 4;  // channel quads (16-byte pieces) per head-pixel
+  constexpr int NQ = D / 4 / SPLIT;  // channel quads (16-byte pieces) of a head-pixel owned by this thread
   constexpr int PX_BYTES = D * 4;
   constexpr int PC = 4;  // samples prepared together (P is a multiple of 4)
   constexpr unsigned FULL = 0xffffffffu;
@@ -96,7 +101,8 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
 
   // ---- this thread's (query, head) pair ----
   const int TP = prm.TH * prm.TW;
-  const int r = threadIdx.x / TP, pos = threadIdx.x - r * TP;
+  const int t = threadIdx.x / SPLIT, half = threadIdx.x % SPLIT;  // pair index inside the block, channel half
+  const int r = t / TP, pos = t - r * TP;
   const int ty = pos / prm.TW, tx = pos - ty * prm.TW;
   const int y = ty0 + ty, x = tx0 + tx;
   const bool active = r < R && y < H && x < W;
@@ -107,11 +113,12 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
   const float fH = (float)H, fW = (float)W;
 
   // per-lane rotation of the channel quads (bank-conflict avoidance, see header): quad k of this thread's
-  // accumulator holds channels 4*((k+rot)%NQ) .. +3
+  // accumulator holds channels 4*((k+rot)%NQ) .. +3 of its half. SPLIT = 2: lane = 2 * pixel + half, a quarter-warp
+  // covers 4 pixels x 2 halves = 8 distinct 16-byte bank groups of the 128-byte pixel pitch.
   const int rot = (NQ >= 8) ? (lane & (NQ - 1)) : (NQ == 4 ? ((lane >> 1) & 3) : ((lane >> 2) & (NQ - 1)));
   int qoff[NQ];  // byte offset of quad k inside a head-pixel
 #pragma unroll
-  for (int k = 0; k < NQ; ++k) qoff[k] = ((k + rot) & (NQ - 1)) * 16;
+  for (int k = 0; k < NQ; ++k) qoff[k] = half * (NQ * 16) + ((k + rot) & (NQ - 1)) * 16;
 
   float4 acc[NQ];
 #pragma unroll
@@ -134,8 +141,8 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
 
     float xy[2 * P], aw[P];
     if (active) {
-      read_record<2 * P>(win + prm.off_a, threadIdx.x, lane, xy);
-      read_record<P>(win + prm.off_b, threadIdx.x, lane, aw);
+      read_record<2 * P>(win + prm.off_a, t, lane, xy);
+      read_record<P>(win + prm.off_b, t, lane, aw);
       if (FUSED) {
         float rf[2 * P];
         read_record<2 * P>(win + prm.off_ref, pos, lane, rf);
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(kMaxThreads, (D >= 32 || P >= 8) ? 1 : 2)
 
 template <int D, int P, bool FUSED>
 int launch_vg(const CUtensorMap* maps, const VgParams& prm, const VgPlan& pl, int tiles, int B, cudaStream_t st) {
-  auto kern = msda_vg_kernel<D, P, FUSED>;
+  auto kern = msda_vg_kernel<D, P, FUSED, (D >= 32 ? 2 : 1)>;
   MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   dim3 grid((unsigned)tiles, (unsigned)prm.M, (unsigned)B);
   kern<<<grid, pl.threads, pl.smem, st>>>(maps[0], maps[1], maps[2], maps[3], prm);
@@ -315,7 +322,9 @@ int viewgrid_dispatch(const float* value, const float* loc, const float* attn, c
                        reinterpret_cast<uintptr_t>(ref);
   if (al & 15u) return MVD_ERR_MISALIGNED;
   VgPlan pl;
-  if (!plan_viewgrid(D, R, P, FUSED, &pl, viewgrid_halo(P))) return MVD_ERR_UNSUPPORTED;
+  const int split = D >= 32 ? 2 : 1;  // must match launch_vg
+  if (!plan_viewgrid(D, R, P, FUSED, &pl, viewgrid_halo(P), split, split == 2 ? kMaxThreadsSplit : kMaxThreads))
+    return MVD_ERR_UNSUPPORTED;
   pl.tiles_x = (W + pl.TW - 1) / pl.TW;
   pl.tiles_y = (H + pl.TH - 1) / pl.TH;
 

@@ -120,18 +120,20 @@ inline uint32_t up128(size_t v) { return (uint32_t)((v + 127) & ~(size_t)127); }
 
 // Tile = TH x TW ground cells with TH*TW*R <= kMaxThreads threads; prefers 64 cells (4x16), 32 (4x8) for many views; the
 // tile is narrowed further while two stages of window + records do not fit the shared memory of one block.
-bool plan_viewgrid(int D, int R, int P, bool fused, VgPlan* pl, int halo = kHalo) {
+// `split` threads share one (query, head) pair (each owns D / split channels); `max_threads` is the block-size limit.
+bool plan_viewgrid(int D, int R, int P, bool fused, VgPlan* pl, int halo = kHalo, int split = 1,
+                   int max_threads = kMaxThreads) {
   int TH = 4, TW = 16;
-  while (TH * TW * R > kMaxThreads && TW > 4) TW >>= 1;
-  while (TH * TW * R > kMaxThreads && TH > 1) TH >>= 1;
-  if (TH * TW * R > kMaxThreads || R > 256) return false;
+  while (TH * TW * R * split > max_threads && TW > 4) TW >>= 1;
+  while (TH * TW * R * split > max_threads && TH > 1) TH >>= 1;
+  if (TH * TW * R * split > max_threads || R > 256) return false;
   for (;; TW >>= 1) {
     pl->TH = TH;
     pl->TW = TW;
     pl->halo = halo;
     pl->BW = TW + 2 * halo;
     pl->BH = TH + 2 * halo;
-    pl->threads = ((TH * TW * R + 31) / 32) * 32;
+    pl->threads = ((TH * TW * R * split + 31) / 32) * 32;
     const size_t nbox = (size_t)TH * TW * R;
     const size_t win = (size_t)pl->BW * pl->BH * D * 4, a = nbox * 2 * P * 4, b = nbox * P * 4,
                  rf = fused ? (size_t)TH * TW * 2 * P * 4 : 0;
