@@ -115,6 +115,10 @@ __device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& 
   split2(v.z, v.w, t0.w, t1.w, t2.w);
 }
 
+// elect_one() (vg_common.cuh): one leader lane of a CONVERGED warp. r02p (ncu source page): with the whole issue loop under `if (lane == 0)` the
+// compiler could not prove the operands of the uniform-datapath instructions (UTCHMMA, UTCBAR, UTMALDG) warp-uniform and
+// wrapped every one in an ELECT / R2UR / BRA.U.ANY waterfall; the MMA warp spent two thirds of its time issuing and the
+// tensor pipe idled at 36 %. The loops now run on all 32 lanes and only the asynchronous instructions sit under elect.
 __global__ void __launch_bounds__(kBThreads, 1)
     linear_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                          const GbParams prm) {
@@ -170,43 +174,44 @@ __global__ void __launch_bounds__(kBThreads, 1)
   const int ntiles = prm.m_blocks * prm.n_tiles;
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer ------------------------------------------------
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (tile / prm.n_tiles) * kBM, n0 = (tile % prm.n_tiles) * kBN;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const uint32_t rs = it % kRawStages, ws = it % kWStages;
-          mbar_wait(b_raw_empty + 8u * rs, ((it / kRawStages) & 1u) ^ 1u);  // first lap: passes at once
+    // ------------------------------------------------ TMA producer (converged warp, elected lane issues) ------------
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int m0 = (tile / prm.n_tiles) * kBM, n0 = (tile % prm.n_tiles) * kBN;
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const uint32_t rs = it % kRawStages, ws = it % kWStages;
+        mbar_wait(b_raw_empty + 8u * rs, ((it / kRawStages) & 1u) ^ 1u);  // first lap: passes at once
+        mbar_wait(b_w_empty + 8u * ws, ((it / kWStages) & 1u) ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
           tma_load_2d_b(base + kOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
-          mbar_wait(b_w_empty + 8u * ws, ((it / kWStages) & 1u) ^ 1u);
           mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)(3 * kHalfBytes));
 #pragma unroll
           for (int i = 0; i < 3; ++i)
             tma_load_3d(base + kOffW + (ws * 3 + i) * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer --------------------------------------------------
-    if (lane == 0) {
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
-        const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
-        mbar_wait(b_acc_empty + 8u * b, tph ^ 1u);  // the epilogue has drained this accumulator (first two tiles: at once)
+    // ------------------------------------------------ MMA issuer (converged warp, elected lane issues) --------------
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const uint32_t b = tcount & 1u, tph = (tcount >> 1) & 1u;
+      mbar_wait(b_acc_empty + 8u * b, tph ^ 1u);  // the epilogue has drained this accumulator (first two tiles: at once)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // two accumulators per tile: the tensor core's fp32 accumulation truncates (~0.5 ulp of the ACCUMULATOR per
+      // instruction, r02e: error grew with the number of MMAs, 6 per k-step). The leading product a0*b0 gets its own
+      // accumulator (K/16 additions); the five small products (2^-8 and below) go to a second one whose rounding is
+      // 2^-8 smaller. The epilogue adds the two in fp32.
+      const uint32_t acc_hi = tmem + b * (uint32_t)(2 * kBN), acc_lo = acc_hi + (uint32_t)kBN;
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const uint32_t ws = it % kWStages, ts = it % kTStages;
+        mbar_wait(b_w_full + 8u * ws, (it / kWStages) & 1u);  // weight terms landed
+        mbar_wait(b_t_full + 8u * ts, (it / kTStages) & 1u);  // x terms written by all 128 splitter threads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // two accumulators per tile: the tensor core's fp32 accumulation truncates (~0.5 ulp of the ACCUMULATOR per
-        // instruction, r02e: error grew with the number of MMAs, 6 per k-step). The leading product a0*b0 gets its own
-        // accumulator (K/16 additions); the five small products (2^-8 and below) go to a second one whose rounding is
-        // 2^-8 smaller. The epilogue adds the two in fp32.
-        const uint32_t acc_hi = tmem + b * (uint32_t)(2 * kBN), acc_lo = acc_hi + (uint32_t)kBN;
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const uint32_t ws = it % kWStages, ts = it % kTStages;
-          mbar_wait(b_w_full + 8u * ws, (it / kWStages) & 1u);  // weight terms landed
-          mbar_wait(b_t_full + 8u * ts, (it / kTStages) & 1u);  // x terms written by all 128 splitter threads
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = base + kOffT + ts * 3 * kHalfBytes, b0 = base + kOffW + ws * 3 * kHalfBytes;
+        const uint32_t a0 = base + kOffT + ts * 3 * kHalfBytes, b0 = base + kOffW + ws * 3 * kHalfBytes;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {  // UMMA K = 16 bf16 = 32 bytes inside the 64-byte swizzle row
             const uint32_t ko = 32u * (uint32_t)k;
@@ -226,8 +231,9 @@ __global__ void __launch_bounds__(kBThreads, 1)
           }
           umma_commit(b_w_empty + 8u * ws);  // both operand stages reusable once these MMAs have read them
           umma_commit(b_t_empty + 8u * ts);
+          if (kc == nk - 1) umma_commit(b_acc_full + 8u * b);  // accumulator complete
         }
-        umma_commit(b_acc_full + 8u * b);  // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -489,54 +495,57 @@ __global__ void __launch_bounds__(kTsThreads, 1)
   const int a_loads = reuse ? nk : prm.n_tiles * nk;  // x chunks loaded and split per row block
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer: fp32 x tiles -----------------------------------
-    if (lane == 0) {
-      uint32_t ia = 0;
-      for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
-        const int m0 = mb * kBM;
-        for (int l = 0; l < a_loads; ++l, ++ia) {
-          const int kc = l % nk;
-          const uint32_t rs = ia % kTsRawStages;
-          mbar_wait(b_raw_empty + 8u * rs, ((ia / kTsRawStages) & 1u) ^ 1u);  // first lap: passes at once
+    // ------------------------------------------------ TMA producer: fp32 x tiles (converged warp, elected lane) -----
+    uint32_t ia = 0;
+    for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
+      const int m0 = mb * kBM;
+      for (int l = 0; l < a_loads; ++l, ++ia) {
+        const int kc = l % nk;
+        const uint32_t rs = ia % kTsRawStages;
+        mbar_wait(b_raw_empty + 8u * rs, ((ia / kTsRawStages) & 1u) ^ 1u);  // first lap: passes at once
+        if (elect_one()) {
           mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
           tma_load_2d_b(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 14) {
     // ------------------------------------------------ TMA producer: weight terms (one chunk per column tile and k) --
-    if (lane == 0) {
-      uint32_t iw = 0;
-      for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
-        for (int nt = 0; nt < prm.n_tiles; ++nt) {
-          const int n0 = nt * kBN;
-          for (int kc = 0; kc < nk; ++kc, ++iw) {
-            const uint32_t ws = iw % kTsWStages;
-            mbar_wait(b_w_empty + 8u * ws, ((iw / kTsWStages) & 1u) ^ 1u);
+    uint32_t iw = 0;
+    for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
+      for (int nt = 0; nt < prm.n_tiles; ++nt) {
+        const int n0 = nt * kBN;
+        for (int kc = 0; kc < nk; ++kc, ++iw) {
+          const uint32_t ws = iw % kTsWStages;
+          mbar_wait(b_w_empty + 8u * ws, ((iw / kTsWStages) & 1u) ^ 1u);
+          if (elect_one()) {
             mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)kWBytes);
 #pragma unroll
             for (int i = 0; i < NT; ++i)
               tma_load_3d(base + kTsOffW + ws * kWBytes + i * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer --------------------------------------------------
-    if (lane == 0) {
-      uint32_t ia_base = 0, iw = 0, tcount = 0;
-      const uint32_t acc_hi = tmem, acc_lo = tmem + (uint32_t)kBN;
-      for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
-        for (int nt = 0; nt < prm.n_tiles; ++nt, ++tcount) {
-          mbar_wait(b_acc_empty, (tcount & 1u) ^ 1u);  // the epilogue holds the previous tile in registers (first tile: at once)
+    // ------------------------------------------------ MMA issuer (converged warp, one elected lane issues) ---------
+    uint32_t ia_base = 0, iw = 0, tcount = 0;
+    const uint32_t acc_hi = tmem, acc_lo = tmem + (uint32_t)kBN;
+    for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
+      for (int nt = 0; nt < prm.n_tiles; ++nt, ++tcount) {
+        mbar_wait(b_acc_empty, (tcount & 1u) ^ 1u);  // the epilogue holds the previous tile in registers (first tile: at once)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kc = 0; kc < nk; ++kc, ++iw) {
+          const uint32_t a_idx = ia_base + (uint32_t)(reuse ? kc : nt * nk + kc);
+          const uint32_t as = a_idx % kTsAStages, ws = iw % kTsWStages;
+          if (!reuse || nt == 0) mbar_wait(b_a_full + 8u * as, (a_idx / kTsAStages) & 1u);  // x terms stored by 128 threads
+          mbar_wait(b_w_full + 8u * ws, (iw / kTsWStages) & 1u);                              // weight terms landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kc = 0; kc < nk; ++kc, ++iw) {
-            const uint32_t a_idx = ia_base + (uint32_t)(reuse ? kc : nt * nk + kc);
-            const uint32_t as = a_idx % kTsAStages, ws = iw % kTsWStages;
-            if (!reuse || nt == 0) mbar_wait(b_a_full + 8u * as, (a_idx / kTsAStages) & 1u);  // x terms stored by 128 threads
-            mbar_wait(b_w_full + 8u * ws, (iw / kTsWStages) & 1u);                              // weight terms landed
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = tmem + kTsAccCols + as * kTsAStageCols, b0 = base + kTsOffW + ws * kWBytes;
+          const uint32_t a0 = tmem + kTsAccCols + as * kTsAStageCols, b0 = base + kTsOffW + ws * kWBytes;
+          const bool release_a = !reuse || nt == prm.n_tiles - 1;  // last column tile: x stage reusable
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) {  // UMMA K = 16 bf16: 8 tensor-memory columns of A, 32 bytes of a W row
               uint32_t ta[NT];
@@ -560,12 +569,13 @@ __global__ void __launch_bounds__(kTsThreads, 1)
               umma_ts<IDESC>(acc_hi, ta[0], db[0], (kc | k) != 0);
             }
             umma_commit(b_w_empty + 8u * ws);
-            if (!reuse || nt == prm.n_tiles - 1) umma_commit(b_a_empty + 8u * as);  // last column tile: x stage reusable
+            if (release_a) umma_commit(b_a_empty + 8u * as);
+            if (kc == nk - 1) umma_commit(b_acc_full);  // accumulator complete
           }
-          umma_commit(b_acc_full);
+          __syncwarp();
         }
-        ia_base += (uint32_t)a_loads;
       }
+      ia_base += (uint32_t)a_loads;
     }
   } else if (warp < 6) {
     // ------------------------------------------------ x-tile splitter (thread = row = tensor-memory lane) ------------

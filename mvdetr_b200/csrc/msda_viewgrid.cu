@@ -94,9 +94,12 @@ __global__ void __launch_bounds__(SPLIT == 2 ? kMaxThreadsSplit : kMaxThreads, (
   for (uint32_t i = threadIdx.x * 16u; i < prm.zero_bytes; i += blockDim.x * 16u)
     *reinterpret_cast<float4*>(smem_raw + prm.zero_off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    issue_level(0);
-    if (L > 1) issue_level(1);
+  if (warp == 0) {
+    if (elect_one()) {
+      issue_level(0);
+      if (L > 1) issue_level(1);
+    }
+    __syncwarp();
   }
 
   // ---- this thread's (query, head) pair ----
@@ -204,7 +207,8 @@ __global__ void __launch_bounds__(SPLIT == 2 ? kMaxThreadsSplit : kMaxThreads, (
         // false for NaN and for threads without a query (tile overhang): those behave like outside samples
         const bool v = active && h_im > -1.f && w_im > -1.f && h_im < fH && w_im < fW;
         const float hf = floorf(h_im), wf = floorf(w_im);
-        const int h0 = v ? (int)hf : 0, w0 = v ? (int)wf : 0;
+        // float -> int conversion saturates (NaN -> 0): for samples outside the level h0 / w0 only pick a bank group below
+        const int h0 = (int)hf, w0 = (int)wf;
         const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
         // a sample outside the level (or outside the window) contributes exactly 0 to the window pass: zero weights on
         // the zero pad (never NaN * 0)
@@ -214,11 +218,11 @@ __global__ void __launch_bounds__(SPLIT == 2 ? kMaxThreadsSplit : kMaxThreads, (
         w2[i] = in ? hh * lw * a : 0.f;
         w3[i] = in ? lh * hw * a : 0.f;
         w4[i] = in ? lh * lw * a : 0.f;
-        // zero-pad reads keep the bank group of the lane's would-be window address (same offset mod 128): r02i ncu source
-        // page: every corner load carried ~12 % excess wavefronts, the border warps whose out-of-level lanes all hit ONE
-        // zero-pad address and collided with a neighbour's window read
-        const int nat = (dy * BW + dx) * PX_BYTES;
-        off[i] = in ? nat : zoff + (nat & 127);
+        // zero-pad reads keep the bank group of the lane's would-be window address (its true position, offset mod 128).
+        // r02i/r02o ncu source page: every corner load carried ~12 % excess wavefronts -- in the border warps the lanes
+        // whose sample leaves the level all read ONE zero-pad address, which collided with a neighbour's window read.
+        const unsigned nat = ((unsigned)dy * (unsigned)BW + (unsigned)dx) * (unsigned)PX_BYTES;
+        off[i] = in ? (int)nat : zoff + (int)(nat & 127u);
         far |= (unsigned)(v && !in) << i;
       }
       // ---- window path, branch-free: far samples were given zero weights on the zero pad ----
@@ -272,10 +276,11 @@ __global__ void __launch_bounds__(SPLIT == 2 ? kMaxThreadsSplit : kMaxThreads, (
     // ---- release the stage; one warp (rotating) refills it with level l+2 once every warp has released it ----
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8u * s);
-    if (l + 2 < L && warp == l % nwarps && lane == 0) {
+    if (l + 2 < L && warp == l % nwarps) {  // converged warp; the TMA instructions under elect (no uniform-register waterfall)
       mbar_wait(bar_empty + 8u * s, ph);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of this stage -> async-proxy refill
-      issue_level(l + 2);
+      if (elect_one()) issue_level(l + 2);
+      __syncwarp();
     }
   }
 

@@ -353,28 +353,34 @@ __global__ void __launch_bounds__(kWtThreads, 2) warp_tma_cl_kernel(const __grid
   s_off[tid] = valid ? ((t.y0 - ymin) * bbw + (t.x0 - xmin)) : -1;
   reinterpret_cast<float4*>(s_w)[tid] = valid ? make_float4(t.nw, t.ne, t.sw, t.se) : make_float4(0.f, 0.f, 0.f, 0.f);
 
-  auto issue_chunk = [&](int ch) {  // one thread: channels [ch*CH, (ch+1)*CH) of the patch -> raw stage ch & 1
+  // whole warp 0, converged: channels [ch*CH, (ch+1)*CH) of the patch -> raw stage ch & 1. Only the TMA instructions sit
+  // under elect (a loop under `tid == 0` made the compiler wrap every UTMALDG in a uniform-register waterfall).
+  auto issue_chunk = [&](int ch) {
     const uint32_t bar = bar0 + 8u * (uint32_t)(ch & 1);
     const uint32_t st = smem_u32(raw + (size_t)(ch & 1) * kWcRaw);
     const uint32_t box_bytes = (uint32_t)(bw * kWtRows * kWcBoxCh * 4);
     const int nb = CH / kWcBoxCh;
-    mbar_expect_tx(bar, (uint32_t)nb * (uint32_t)hg * box_bytes);
+    const bool leader = elect_one();
+    if (leader) mbar_expect_tx(bar, (uint32_t)nb * (uint32_t)hg * box_bytes);
     for (int g = 0; g < hg; ++g)
       for (int b = 0; b < nb; ++b)  // raw layout: [row group g][channel][4 rows][bw]
       {  // the tensor map operand is named statically (one case per box width), never a computed address
         const uint32_t dst = st + (uint32_t)(g * nb + b) * box_bytes;
         const int cy = ymin + g * kWtRows, cc = ch * CH + b * kWcBoxCh;
-        switch (bsel) {
-          case 0: tma_load_4d(dst, &maps.m[0], bar, xmin, cy, cc, n); break;
-          case 1: tma_load_4d(dst, &maps.m[1], bar, xmin, cy, cc, n); break;
-          case 2: tma_load_4d(dst, &maps.m[2], bar, xmin, cy, cc, n); break;
-          case 3: tma_load_4d(dst, &maps.m[3], bar, xmin, cy, cc, n); break;
-          case 4: tma_load_4d(dst, &maps.m[4], bar, xmin, cy, cc, n); break;
-          default: tma_load_4d(dst, &maps.m[5], bar, xmin, cy, cc, n); break;
+        if (leader) {
+          switch (bsel) {
+            case 0: tma_load_4d(dst, &maps.m[0], bar, xmin, cy, cc, n); break;
+            case 1: tma_load_4d(dst, &maps.m[1], bar, xmin, cy, cc, n); break;
+            case 2: tma_load_4d(dst, &maps.m[2], bar, xmin, cy, cc, n); break;
+            case 3: tma_load_4d(dst, &maps.m[3], bar, xmin, cy, cc, n); break;
+            case 4: tma_load_4d(dst, &maps.m[4], bar, xmin, cy, cc, n); break;
+            default: tma_load_4d(dst, &maps.m[5], bar, xmin, cy, cc, n); break;
+          }
         }
       }
+    __syncwarp();
   };
-  if (staged && tid == 0) {
+  if (staged && warp == 0) {
     issue_chunk(0);
     if (nchunks > 1) issue_chunk(1);
   }
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) warp_tma_cl_kernel(const __grid
         }
       }
       __syncthreads();
-      if (tid == 0 && ch + 2 < nchunks) {  // the raw stage is free again
+      if (warp == 0 && ch + 2 < nchunks) {  // the raw stage is free again
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         issue_chunk(ch + 2);
       }
