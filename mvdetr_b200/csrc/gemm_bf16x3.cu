@@ -25,6 +25,9 @@
 //   warps 6-9   epilogue: tcgen05.ld 32 lanes x 16 columns of both accumulators, sum + bias, ReLU, 16-byte stores of
 //               their own rows, overlapping the next tile's main loop (2 x 2 x 128 accumulator columns in tensor memory).
 #include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -55,6 +58,7 @@ struct GbParams {
   int rows, K, N, relu;
   int m_blocks, n_tiles;
   int multicast;  // != 0: `out` is an NVLink multicast address (multimem.st: the NVSwitch replicates every store to all GPUs)
+  int raw_stages, w_stages;  // TS kernels: depth of the fp32 x-tile ring and of the weight-term ring
 };
 
 __device__ __forceinline__ void tma_load_2d_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -373,18 +377,17 @@ constexpr uint32_t kTsTmemCols = 512;
 // their own producer warps and the x ring takes all the shared memory that is left.
 template <int NT>
 struct TsCfg {
-  static constexpr int kRaw = NT == 2 ? 8 : 7;               // fp32 x tiles in flight (16 KB each)
-  static constexpr int kW = 3;                               // weight-term stages (L2-resident source)
+  static constexpr int kRaw = NT == 2 ? 5 : 5;               // default depth of the fp32 x-tile ring (16 KB each)
+  static constexpr int kW = NT == 2 ? 6 : 4;                 // default depth of the weight-term ring (NT x 8 KB each)
+  static constexpr int kMaxRing = 12;
   static constexpr int kA = NT == 2 ? 8 : 5;                 // x-term stages in tensor memory
   static constexpr uint32_t kAStageCols = NT * 16;           // NT terms x 16 columns (32 k of one row per lane)
   static constexpr int kWBytes = NT * kHalfBytes;
-  static constexpr int kOffRaw = 0;
-  static constexpr int kOffW = kOffRaw + kRaw * kRawBytes;
-  static constexpr int kOffStage = kOffW + kW * kWBytes;
-  static constexpr int kSmem = kOffStage + 8 * 32 * kStagePitch * 4 + 1024;  // NT=2: 213 KB, NT=3: 221 KB
-  static constexpr int kNumBars = 2 * kRaw + 2 * kW + 2 * kA + 2;
+  static constexpr int kStageBytes = 8 * 32 * kStagePitch * 4;  // epilogue transposition stages
+  static constexpr int smem(int raw, int w) { return raw * kRawBytes + w * kWBytes + kStageBytes + 1024; }
+  static constexpr int kNumBars = 4 * kMaxRing + 2 * kA + 2;
   static_assert(kTsAccCols + kA * kAStageCols <= kTsTmemCols, "tensor memory");
-  static_assert(kSmem <= 227 * 1024, "shared memory");
+  static_assert(smem(kRaw, kW) <= 227 * 1024, "shared memory");
 };
 
 // fp16 operands (format 0) instead of bf16 (format 1): the two-term variant below
@@ -441,9 +444,10 @@ __global__ void __launch_bounds__(kTsThreads, 1)
                            const GbParams prm) {
   constexpr uint32_t IDESC = NT == 3 ? kIdescBf16 : kIdescF16;
   using Cfg = TsCfg<NT>;
-  constexpr int kTsRawStages = Cfg::kRaw, kTsWStages = Cfg::kW, kTsAStages = Cfg::kA;
+  constexpr int kTsAStages = Cfg::kA, kWBytes = Cfg::kWBytes;
   constexpr uint32_t kTsAStageCols = Cfg::kAStageCols;
-  constexpr int kTsOffRaw = Cfg::kOffRaw, kTsOffW = Cfg::kOffW, kTsOffStage = Cfg::kOffStage, kWBytes = Cfg::kWBytes;
+  const int kTsRawStages = prm.raw_stages, kTsWStages = prm.w_stages;  // ring depths chosen by the host (shared memory split)
+  const int kTsOffRaw = 0, kTsOffW = kTsRawStages * kRawBytes, kTsOffStage = kTsOffW + kTsWStages * kWBytes;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) unsigned long long s_bar[TsCfg<NT>::kNumBars];
   __shared__ uint32_t s_tmem;
@@ -496,29 +500,28 @@ __global__ void __launch_bounds__(kTsThreads, 1)
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer: fp32 x tiles (converged warp, elected lane) -----
-    uint32_t ia = 0;
+    uint32_t rs = 0, rph = 0;  // ring stage, lap parity
     for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
       const int m0 = mb * kBM;
-      for (int l = 0; l < a_loads; ++l, ++ia) {
-        const int kc = l % nk;
-        const uint32_t rs = ia % kTsRawStages;
-        mbar_wait(b_raw_empty + 8u * rs, ((ia / kTsRawStages) & 1u) ^ 1u);  // first lap: passes at once
+      for (int l = 0, kc = 0; l < a_loads; ++l) {
+        mbar_wait(b_raw_empty + 8u * rs, rph ^ 1u);  // first lap: passes at once
         if (elect_one()) {
           mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
           tma_load_2d_b(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
         }
         __syncwarp();
+        if (++kc == nk) kc = 0;
+        if (++rs == (uint32_t)kTsRawStages) rs = 0, rph ^= 1u;
       }
     }
   } else if (warp == 14) {
     // ------------------------------------------------ TMA producer: weight terms (one chunk per column tile and k) --
-    uint32_t iw = 0;
+    uint32_t ws = 0, wph = 0;
     for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
       for (int nt = 0; nt < prm.n_tiles; ++nt) {
         const int n0 = nt * kBN;
-        for (int kc = 0; kc < nk; ++kc, ++iw) {
-          const uint32_t ws = iw % kTsWStages;
-          mbar_wait(b_w_empty + 8u * ws, ((iw / kTsWStages) & 1u) ^ 1u);
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(b_w_empty + 8u * ws, wph ^ 1u);
           if (elect_one()) {
             mbar_expect_tx(b_w_full + 8u * ws, (uint32_t)kWBytes);
 #pragma unroll
@@ -526,22 +529,23 @@ __global__ void __launch_bounds__(kTsThreads, 1)
               tma_load_3d(base + kTsOffW + ws * kWBytes + i * kHalfBytes, &tm_b, b_w_full + 8u * ws, kc * kBK, n0, i);
           }
           __syncwarp();
+          if (++ws == (uint32_t)kTsWStages) ws = 0, wph ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (converged warp, one elected lane issues) ---------
-    uint32_t ia_base = 0, iw = 0, tcount = 0;
+    uint32_t ia_base = 0, ws = 0, wph = 0, tcount = 0;
     const uint32_t acc_hi = tmem, acc_lo = tmem + (uint32_t)kBN;
     for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
       for (int nt = 0; nt < prm.n_tiles; ++nt, ++tcount) {
         mbar_wait(b_acc_empty, (tcount & 1u) ^ 1u);  // the epilogue holds the previous tile in registers (first tile: at once)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kc = 0; kc < nk; ++kc, ++iw) {
+        for (int kc = 0; kc < nk; ++kc) {
           const uint32_t a_idx = ia_base + (uint32_t)(reuse ? kc : nt * nk + kc);
-          const uint32_t as = a_idx % kTsAStages, ws = iw % kTsWStages;
+          const uint32_t as = a_idx % kTsAStages;
           if (!reuse || nt == 0) mbar_wait(b_a_full + 8u * as, (a_idx / kTsAStages) & 1u);  // x terms stored by 128 threads
-          mbar_wait(b_w_full + 8u * ws, (iw / kTsWStages) & 1u);                              // weight terms landed
+          mbar_wait(b_w_full + 8u * ws, wph);                                                 // weight terms landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a0 = tmem + kTsAccCols + as * kTsAStageCols, b0 = base + kTsOffW + ws * kWBytes;
           const bool release_a = !reuse || nt == prm.n_tiles - 1;  // last column tile: x stage reusable
@@ -573,6 +577,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
             if (kc == nk - 1) umma_commit(b_acc_full);  // accumulator complete
           }
           __syncwarp();
+          if (++ws == (uint32_t)kTsWStages) ws = 0, wph ^= 1u;
         }
       }
       ia_base += (uint32_t)a_loads;
@@ -581,11 +586,11 @@ __global__ void __launch_bounds__(kTsThreads, 1)
     // ------------------------------------------------ x-tile splitter (thread = row = tensor-memory lane) ------------
     const int r = (warp & 3) * 32 + lane;
     const uint32_t t_lane = tmem + kTsAccCols + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t ia = 0;
+    uint32_t ia = 0, rs = 0, rph = 0;
     for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
       for (int l = 0; l < a_loads; ++l, ++ia) {
-        const uint32_t rs = ia % kTsRawStages, as = ia % kTsAStages;
-        mbar_wait(b_raw_full + 8u * rs, (ia / kTsRawStages) & 1u);          // fp32 tile landed
+        const uint32_t as = ia % kTsAStages;
+        mbar_wait(b_raw_full + 8u * rs, rph);                               // fp32 tile landed
         mbar_wait(b_a_empty + 8u * as, ((ia / kTsAStages) & 1u) ^ 1u);      // the MMAs that read this stage retired
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned char* src = sm + kTsOffRaw + (size_t)rs * kRawBytes + (size_t)r * 128;  // pieces XOR (r & 7)
@@ -614,6 +619,7 @@ __global__ void __launch_bounds__(kTsThreads, 1)
         mbar_arrive(b_raw_empty + 8u * rs);  // raw tile consumed (generic reads only)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(b_a_full + 8u * as);
+        if (++rs == (uint32_t)kTsRawStages) rs = 0, rph ^= 1u;
       }
     }
   } else if (warp < 14) {
@@ -792,9 +798,23 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
   prm.m_blocks = (int)ceil_div64(rows, kBM);
   prm.n_tiles = (int)ceil_div64(N, kBN);
   prm.multicast = multicast;
+  prm.raw_stages = prm.w_stages = 0;
   if (ts) {  // persistent over row blocks; the column tiles of a row block run back to back on one SM
     auto kern = terms == 3 ? linear_split_ts_kernel<3> : linear_split_ts_kernel<2>;
-    const int smem = terms == 3 ? TsCfg<3>::kSmem : TsCfg<2>::kSmem;
+    // ring depths: defaults of TsCfg, or MVD_GEMM_RINGS="raw,w" (tuning aid; must fit 227 KB and 12 stages each)
+    static int env_raw = -1, env_w = -1;
+    if (env_raw < 0) {
+      int r = 0, w = 0;
+      const char* e = getenv("MVD_GEMM_RINGS");
+      if (!e || sscanf(e, "%d,%d", &r, &w) != 2) r = w = 0;
+      env_w = w;
+      env_raw = r;
+    }
+    prm.raw_stages = env_raw > 0 ? env_raw : (terms == 3 ? TsCfg<3>::kRaw : TsCfg<2>::kRaw);
+    prm.w_stages = env_w > 0 ? env_w : (terms == 3 ? TsCfg<3>::kW : TsCfg<2>::kW);
+    const int smem = terms == 3 ? TsCfg<3>::smem(prm.raw_stages, prm.w_stages) : TsCfg<2>::smem(prm.raw_stages, prm.w_stages);
+    if (prm.raw_stages < 2 || prm.w_stages < 2 || prm.raw_stages > 12 || prm.w_stages > 12 || smem > 227 * 1024)
+      return MVD_ERR_UNSUPPORTED;
     MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned grid = (unsigned)(prm.m_blocks < kNumSMs ? prm.m_blocks : kNumSMs);
     kern<<<grid, kTsThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);

@@ -34,6 +34,7 @@ def timed(fn, flush, iters=20):
 
 
 def main():
+    modes = tuple(os.environ.get("BENCH_GEMM_MODES", "f16x2,bf16x3ts,bf16x3ss,tf32x3,bf16x9,torch").split(","))
     dev = torch.device("cuda:0")
     torch.backends.cuda.matmul.allow_tf32 = False
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -45,9 +46,9 @@ def main():
         exact = x[:4096].double() @ w.double().t() + b.double()
         if relu:
             exact = exact.clamp_min(0)
-        rec = {"name": name, "rows": rows, "K": K, "N": N, "relu": relu,
+        rec = {"rings": os.environ.get("MVD_GEMM_RINGS", "default"), "name": name, "rows": rows, "K": K, "N": N, "relu": relu,
                "hbm_floor_us": 4 * (rows * K + rows * N + N * K) / 6549.8e3}
-        for mode in ("f16x2", "bf16x3ts", "bf16x3ss", "tf32x3", "bf16x9", "torch"):
+        for mode in modes:
             try:
                 out = ops.linear(x, w, b, relu=relu, mode=mode)
                 rec[mode + "_err"] = (out[:4096].double() - exact).abs().max().item()
