@@ -140,6 +140,9 @@ bool plan_viewgrid(int D, int R, int P, bool fused, VgPlan* pl, int halo = kHalo
   while (TH * TW * R * split > max_threads && TW > 4) TW >>= 1;
   while (TH * TW * R * split > max_threads && TH > 1) TH >>= 1;
   if (TH * TW * R * split > max_threads || R > 256) return false;
+  // few views per block (the view-sharded multi-GPU path: R = 1 per rank): 64 threads per window left the SM at 6 warps
+  // (r02l timeline: 57 us per launch for a seventh of the queries). A taller tile doubles the threads per window.
+  if (TH == 4 && 2 * TH * TW * R * split <= max_threads / 2) TH = 8;
   for (;; TW >>= 1) {
     pl->TH = TH;
     pl->TW = TW;

@@ -89,3 +89,23 @@ def test_split_cache_is_keyed_on_the_tensor_object(cuda):
             got = ops.linear(x, w, None, mode=mode)
             assert (got.double() - x.double() @ w.double().t()).abs().max().item() <= 1e-4, (i, mode)
         del w
+
+
+def test_f16x2_range_contract(cuda):
+    """The default two-term fp16 kernel covers operands below 65504 and small ones down to fp16's subnormals with an
+    absolute error far below the 1e-4 bar; beyond the range the result is non-finite (visible), and the three-term bf16
+    kernel (MVDETR_B200_GEMM=bf16x3) takes the full fp32 range."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(300, 128, generator=g).to(cuda)
+    w = (torch.randn(64, 128, generator=g) / 128 ** 0.5).to(cuda)
+    exact = x.double() @ w.double().t()
+    for scale in (1e-6, 1e-3, 1.0, 1e3):   # 1e3 * |x| <= ~5e3 < 65504
+        got = ops.linear(x * scale, w, None, mode="f16x2")
+        err = (got.double() - exact * scale).abs().max().item()
+        assert err <= max(4e-6 * scale * exact.abs().max().item(), 1e-9), (scale, err)
+    big = x.clone()
+    big[5, 7] = 1e6
+    assert not torch.isfinite(ops.linear(big, w, None, mode="f16x2")[5]).all()      # out of fp16 range: loud
+    ok = ops.linear(big, w, None, mode="bf16x3")
+    assert torch.isfinite(ok).all()
+    assert (ok.double() - big.double() @ w.double().t()).abs().max().item() <= 1e-6 * 1e6

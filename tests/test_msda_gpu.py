@@ -228,6 +228,10 @@ def test_host_buffer_entry_point(cuda):
     (6, 9, 50, 4, 32, 8, 6, 1, 5.0),      # D=32, P=8 instantiation
     (2, 5, 7, 3, 8, 4, 1, 1, 2.0),        # D=8, a single replica of a grid smaller than one tile
     (4, 17, 33, 2, 16, 8, 20, 1, 6.0),    # many replicas -> smaller tile
+    (7, 30, 45, 8, 16, 4, 1, 1, 4.0),     # one replica per rank of the view-sharded path -> taller (8 x 16) tile
+    (7, 30, 45, 8, 16, 4, 2, 1, 4.0),     # two replicas (4 GPUs)
+    (8, 20, 36, 8, 32, 8, 8, 1, 8.0),     # BASELINE configs[3] layout: D=32 (two lanes per pair), P=8 -> halo 9
+    (4, 20, 36, 4, 32, 4, 1, 1, 4.0),     # D=32, P=4, one replica
 ])
 def test_viewgrid_kernel_vs_c_oracle(cuda, L, H, W, M, D, P, R, B, offset_px):
     """The TMA-staged view-grid kernel (host-int geometry) against the C oracle and bit-level against nothing less:
