@@ -462,23 +462,23 @@ __global__ void __launch_bounds__(kTsThreads, 1)
   const uint32_t b_a_full = take(kTsAStages), b_a_empty = take(kTsAStages);          // splitters -> MMA -> splitters
   const uint32_t b_acc_full = take(1), b_acc_empty = take(1);                        // MMA -> epilogue -> MMA
 
-  if (tid == 0) {
+  // prologue in parallel: warp 0 allocates tensor memory while the threads of warps 1-3 initialise one barrier each
+  // (one thread doing 40 mbarrier.init in a row ahead of the allocation cost ~1 us of every launch: 21 launches a frame)
+  if (tid == 32) {
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
-    for (int i = 0; i < kTsRawStages; ++i) {
-      mbar_init(b_raw_full + 8u * i, 1);
-      mbar_init(b_raw_empty + 8u * i, 128);
-    }
-    for (int i = 0; i < kTsWStages; ++i) {
-      mbar_init(b_w_full + 8u * i, 1);
-      mbar_init(b_w_empty + 8u * i, 1);
-    }
-    for (int i = 0; i < kTsAStages; ++i) {
-      mbar_init(b_a_full + 8u * i, 128);
-      mbar_init(b_a_empty + 8u * i, 1);
-    }
-    mbar_init(b_acc_full, 1);
-    mbar_init(b_acc_empty, 256);
+  }
+  if (tid >= 32 && tid < 32 + nb) {
+    const int j = tid - 32, R = kTsRawStages, W = kTsWStages, A = kTsAStages;
+    uint32_t count;
+    if (j < R) count = 1;                      // raw_full: the TMA transaction
+    else if (j < 2 * R) count = 128;           // raw_empty: every splitter thread
+    else if (j < 2 * R + 2 * W) count = 1;     // w_full (TMA) / w_empty (tcgen05.commit)
+    else if (j < 2 * R + 2 * W + A) count = 128;     // a_full: every splitter thread
+    else if (j < 2 * R + 2 * W + 2 * A) count = 1;   // a_empty: tcgen05.commit
+    else if (j == 2 * R + 2 * W + 2 * A) count = 1;  // acc_full: tcgen05.commit
+    else count = 256;                          // acc_empty: every epilogue thread
+    mbar_init(bars + 8u * (uint32_t)j, count);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
