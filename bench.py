@@ -596,7 +596,10 @@ def run_ours(args):
                 "roofline": roofline,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "pipeline": "pinned host -> H2D stream / graph replay / D2H stream, 2 slots"},
-                "gpu_launches": our_launches_per_frame(fusion, lt_gemm) * args.steps,
+                # rank 0's own kernels; the view-sharded path adds the multicast copy of the final tokens (the symmetric-
+                # memory barrier kernels and NCCL's are not ours and not counted)
+                "gpu_launches": (our_launches_per_frame(fusion, lt_gemm) + (1 if world > 1 and "multicast" in mode else 0))
+                                * args.steps,
                 "clocks": clocks,
                 "hot_path": {"warp_us": wk["us"], "warp_kernel": wk.get("launches"), "msda_fused_fwd_us": dom["us"],
                              "frames_per_sec_kernels_only": 1e6 / hot_us,
