@@ -353,6 +353,21 @@ MVD_API int mvd_linear_bf16x3_multicast_f32(const float* x, const void* w_terms,
                                     int N, int relu, float* out_mc, void* stream);
 MVD_API int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t rows, int C, int64_t inner,
                            int64_t outer_total, int64_t outer0, void* stream);
+/* 3x3 / pad 1 / stride {1, 2} convolution of a channels-last fp32 image src [NB][Hi][Wi][C] (C % 32 == 0) as an
+ * IMPLICIT GEMM on the same tcgen05 kernel: a row block is a tile of output pixels of one image, a K chunk is 32
+ * channels of one tap fetched by TMA straight from the image (4-D tensor map with traversal stride = conv stride,
+ * out-of-image coordinates zero-filled = the padding). No im2col matrix exists in memory. w_terms: the split of the
+ * [N][9 C] weight matrix with columns ordered (ky, kx, c) (terms = 2: mvd_f16_split2_f32, 3: mvd_bf16_split3_f32).
+ * out [NB * Ho * Wo][N] channels-last, Ho = (Hi - 1) / stride + 1. Bit-identical to mvd_linear_* over the im2col matrix
+ * of mvd_warp_im2col_f32 / mvd_upsample_im2col_f32. Replaces self.downsample and the upsample conv
+ * (ref: multiview_detector/models/trans_world_feat.py:74,82-84,89,109). MVD_ERR_UNSUPPORTED when the output width has
+ * no divisor in [16, 128] (callers keep the im2col route).
+ * mvd_upsample_nhwc_f32: bilinear upsample (align_corners = false, ATen arithmetic) of a channels-last map, output rows
+ * [row0, row0 + nrows) only: the input of that convolution (ref: trans_world_feat.py:83 nn.Upsample). */
+MVD_API int mvd_conv3x3_nhwc_f32(const float* src, const void* w_terms, const float* bias, int NB, int Hi, int Wi, int C,
+                         int stride, int N, int relu, int terms, float* out, void* stream);
+MVD_API int mvd_upsample_nhwc_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, int row0, int nrows,
+                          float* dst, void* stream);
 /* Same two GEMMs (same arguments, bit-identical results) with the three bf16 terms of x staged in TENSOR MEMORY by the
  * splitter warps (tcgen05.st) and consumed by tcgen05.mma's A-from-TMEM form: 40 % less shared-memory traffic per K
  * chunk, and for K <= 128 the terms of a 128-row block are reused by every 128-column tile of the output (x is read and

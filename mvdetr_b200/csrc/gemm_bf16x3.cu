@@ -59,6 +59,10 @@ struct GbParams {
   int m_blocks, n_tiles;
   int multicast;  // != 0: `out` is an NVLink multicast address (multimem.st: the NVSwitch replicates every store to all GPUs)
   int raw_stages, w_stages;  // TS kernels: depth of the fp32 x-tile ring and of the weight-term ring
+  // TS kernels, conv != 0: x is a channels-last image [NB][Hi][Wi][C] and the GEMM is the 3x3 / pad 1 / stride cstride
+  // convolution over it (K = 9 C, taps (ky, kx, c)): a row block is a TY x TX tile of output pixels of one image and a K
+  // chunk is 32 channels of one tap, fetched by TMA straight from the image (no im2col matrix in memory)
+  int conv, cHo, cWo, TX, TY, tiles_x, tiles_y, cchunks, cstride;
 };
 
 __device__ __forceinline__ void tma_load_2d_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -501,13 +505,27 @@ __global__ void __launch_bounds__(kTsThreads, 1)
   if (warp == 0) {
     // ------------------------------------------------ TMA producer: fp32 x tiles (converged warp, elected lane) -----
     uint32_t rs = 0, rph = 0;  // ring stage, lap parity
+    const uint32_t raw_tx = prm.conv ? (uint32_t)(prm.TX * prm.TY * kBK * 4) : (uint32_t)kRawBytes;
     for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
       const int m0 = mb * kBM;
+      int img = 0, xb = 0, yb = 0;  // conv: image, source coordinates of the tile's first output pixel for tap (0, 0)
+      if (prm.conv) {
+        const int tpi = prm.tiles_x * prm.tiles_y;
+        img = mb / tpi;
+        const int t = mb - img * tpi, ty = t / prm.tiles_x, tx = t - ty * prm.tiles_x;
+        xb = tx * prm.TX * prm.cstride - 1;
+        yb = ty * prm.TY * prm.cstride - 1;
+      }
       for (int l = 0, kc = 0; l < a_loads; ++l) {
         mbar_wait(b_raw_empty + 8u * rs, rph ^ 1u);  // first lap: passes at once
         if (elect_one()) {
-          mbar_expect_tx(b_raw_full + 8u * rs, (uint32_t)kRawBytes);
-          tma_load_2d_b(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
+          mbar_expect_tx(b_raw_full + 8u * rs, raw_tx);
+          if (prm.conv) {  // 32 channels of tap (ky, kx): rows of the stage = output pixels (y, x) of the tile, zero padding
+            const int tap = kc / prm.cchunks, cc = kc - tap * prm.cchunks, ky = tap / 3, kx = tap - 3 * ky;
+            tma_load_4d(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, cc * kBK, xb + kx, yb + ky, img);
+          } else {
+            tma_load_2d_b(base + kTsOffRaw + rs * kRawBytes, &tm_a, b_raw_full + 8u * rs, kc * kBK, m0);
+          }
         }
         __syncwarp();
         if (++kc == nk) kc = 0;
@@ -635,7 +653,21 @@ __global__ void __launch_bounds__(kTsThreads, 1)
     const int piece = lane & 7;
     uint32_t tcount = 0;
     for (int mb = blockIdx.x; mb < prm.m_blocks; mb += gridDim.x) {
-      const int r0 = mb * kBM + q * 32;
+      // output row of each of the 8 tile rows this lane stores (row = q * 32 + (lane >> 3) + 4 i), or -1
+      int64_t grow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = q * 32 + (lane >> 3) + 4 * i;
+        if (prm.conv) {
+          const int tpi = prm.tiles_x * prm.tiles_y, img = mb / tpi, t = mb - img * tpi;
+          const int ty = t / prm.tiles_x, tx = t - ty * prm.tiles_x;
+          const int yl = r / prm.TX, xl = r - yl * prm.TX, yo = ty * prm.TY + yl;
+          grow[i] = (yl < prm.TY && yo < prm.cHo) ? ((int64_t)img * prm.cHo + yo) * prm.cWo + tx * prm.TX + xl : -1;
+        } else {
+          const int64_t g = (int64_t)mb * kBM + r;
+          grow[i] = g < prm.rows ? g : -1;
+        }
+      }
       for (int nt = 0; nt < prm.n_tiles; ++nt, ++tcount) {
         const int n0 = nt * kBN + half * 64 + piece * 4;  // first column of this lane's piece in column block 0
         float4 bb[2];
@@ -677,7 +709,6 @@ __global__ void __launch_bounds__(kTsThreads, 1)
               xs[i] = *reinterpret_cast<const float4*>(stg + ((lane >> 3) + 4 * i) * kStagePitch + piece * 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int rr = (lane >> 3) + 4 * i;
               float4 x = xs[i];
               x.x += bb[cb].x;
               x.y += bb[cb].y;
@@ -689,8 +720,8 @@ __global__ void __launch_bounds__(kTsThreads, 1)
                 x.z = fmaxf(x.z, 0.f);
                 x.w = fmaxf(x.w, 0.f);
               }
-              if (r0 + rr < prm.rows) {
-                float* dst = prm.out + (int64_t)(r0 + rr) * prm.N + n;
+              if (grow[i] >= 0) {
+                float* dst = prm.out + grow[i] * prm.N + n;
                 if (prm.multicast)
                   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x),
                                "f"(x.y), "f"(x.z), "f"(x.w)
@@ -757,6 +788,44 @@ extern "C" int mvd_bf16_split3_f32(const float* w, int64_t n, void* terms, void*
   return MVD_OK;
 }
 
+static int encode_w_terms(CUtensorMap* tm_b, const void* w_terms, int K, int N, int terms) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return MVD_ERR_NO_DEVICE;
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)terms};
+  const cuuint64_t gstr[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBN, 1u};
+  if (enc(tm_b, terms == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+          const_cast<void*>(w_terms), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return MVD_ERR_UNSUPPORTED;
+  return MVD_OK;
+}
+
+// persistent over row blocks; the column tiles of a row block run back to back on one SM
+static int launch_ts(const CUtensorMap& tm_a, const CUtensorMap& tm_b, GbParams& prm, int terms, void* stream) {
+  auto kern = terms == 3 ? linear_split_ts_kernel<3> : linear_split_ts_kernel<2>;
+  // ring depths: defaults of TsCfg, or MVD_GEMM_RINGS="raw,w" (tuning aid; must fit 227 KB and 12 stages each)
+  static int env_raw = -1, env_w = -1;
+  if (env_raw < 0) {
+    int r = 0, w = 0;
+    const char* e = getenv("MVD_GEMM_RINGS");
+    if (!e || sscanf(e, "%d,%d", &r, &w) != 2) r = w = 0;
+    env_w = w;
+    env_raw = r;
+  }
+  prm.raw_stages = env_raw > 0 ? env_raw : (terms == 3 ? TsCfg<3>::kRaw : TsCfg<2>::kRaw);
+  prm.w_stages = env_w > 0 ? env_w : (terms == 3 ? TsCfg<3>::kW : TsCfg<2>::kW);
+  const int smem = terms == 3 ? TsCfg<3>::smem(prm.raw_stages, prm.w_stages) : TsCfg<2>::smem(prm.raw_stages, prm.w_stages);
+  if (prm.raw_stages < 2 || prm.w_stages < 2 || prm.raw_stages > 12 || prm.w_stages > 12 || smem > 227 * 1024)
+    return MVD_ERR_UNSUPPORTED;
+  MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const unsigned grid = (unsigned)(prm.m_blocks < kNumSMs ? prm.m_blocks : kNumSMs);
+  kern<<<grid, kTsThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
+
 static int linear_bf16x3(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N, int relu,
                          float* out, int multicast, int ts, void* stream, int terms = 3) {
   if (!x || !w_terms || !out) return MVD_ERR_NULL_POINTER;
@@ -768,8 +837,8 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return MVD_ERR_NO_DEVICE;
   alignas(64) CUtensorMap tm_a, tm_b;
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
   {
+    const cuuint32_t estr[2] = {1u, 1u};
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
     const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
@@ -778,17 +847,8 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return MVD_ERR_UNSUPPORTED;
   }
-  {
-    const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)terms};
-    const cuuint64_t gstr[2] = {(cuuint64_t)K * 2, (cuuint64_t)N * K * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBN, 1u};
-    if (enc(&tm_b, terms == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
-            const_cast<void*>(w_terms), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return MVD_ERR_UNSUPPORTED;
-  }
-  GbParams prm;
+  if (int e = encode_w_terms(&tm_b, w_terms, K, N, terms)) return e;
+  GbParams prm = {};
   prm.bias = bias;
   prm.out = out;
   prm.rows = (int)rows;
@@ -798,34 +858,75 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
   prm.m_blocks = (int)ceil_div64(rows, kBM);
   prm.n_tiles = (int)ceil_div64(N, kBN);
   prm.multicast = multicast;
-  prm.raw_stages = prm.w_stages = 0;
-  if (ts) {  // persistent over row blocks; the column tiles of a row block run back to back on one SM
-    auto kern = terms == 3 ? linear_split_ts_kernel<3> : linear_split_ts_kernel<2>;
-    // ring depths: defaults of TsCfg, or MVD_GEMM_RINGS="raw,w" (tuning aid; must fit 227 KB and 12 stages each)
-    static int env_raw = -1, env_w = -1;
-    if (env_raw < 0) {
-      int r = 0, w = 0;
-      const char* e = getenv("MVD_GEMM_RINGS");
-      if (!e || sscanf(e, "%d,%d", &r, &w) != 2) r = w = 0;
-      env_w = w;
-      env_raw = r;
-    }
-    prm.raw_stages = env_raw > 0 ? env_raw : (terms == 3 ? TsCfg<3>::kRaw : TsCfg<2>::kRaw);
-    prm.w_stages = env_w > 0 ? env_w : (terms == 3 ? TsCfg<3>::kW : TsCfg<2>::kW);
-    const int smem = terms == 3 ? TsCfg<3>::smem(prm.raw_stages, prm.w_stages) : TsCfg<2>::smem(prm.raw_stages, prm.w_stages);
-    if (prm.raw_stages < 2 || prm.w_stages < 2 || prm.raw_stages > 12 || prm.w_stages > 12 || smem > 227 * 1024)
-      return MVD_ERR_UNSUPPORTED;
-    MVD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const unsigned grid = (unsigned)(prm.m_blocks < kNumSMs ? prm.m_blocks : kNumSMs);
-    kern<<<grid, kTsThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
-  } else {
-    MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
-    const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;
-    const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
-    linear_bf16x3_kernel<<<grid, kBThreads, kBSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
-  }
+  if (ts) return launch_ts(tm_a, tm_b, prm, terms, stream);
+  MVD_CUDA_TRY(cudaFuncSetAttribute(linear_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmem));
+  const int64_t tiles = (int64_t)prm.m_blocks * prm.n_tiles;
+  const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+  linear_bf16x3_kernel<<<grid, kBThreads, kBSmem, (cudaStream_t)stream>>>(tm_a, tm_b, prm);
   MVD_LAUNCH_CHECK();
   return MVD_OK;
+}
+
+// 3x3 / pad 1 / stride {1, 2} convolution of a channels-last image as an implicit GEMM on the TS kernel: no im2col
+// matrix. Output [NB * Ho * Wo, N] (channels-last). Bit-identical to mvd_linear_* over the (ky, kx, c)-ordered im2col
+// matrix of the same image: the K chunks, their order and the accumulators are the same.
+static int conv3x3_nhwc(const float* src, const void* w_terms, const float* bias, int NB, int Hi, int Wi, int C,
+                        int stride, int N, int relu, int terms, float* out, int multicast, void* stream) {
+  if (!src || !w_terms || !out) return MVD_ERR_NULL_POINTER;
+  if (NB <= 0 || Hi <= 0 || Wi <= 0 || C <= 0 || N <= 0) return MVD_ERR_BAD_SHAPE;
+  if ((stride != 1 && stride != 2) || (terms != 2 && terms != 3)) return MVD_ERR_BAD_SHAPE;
+  if (C % kBK != 0 || N % 4 != 0) return MVD_ERR_UNSUPPORTED;  // a K chunk is 32 channels of one tap
+  const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(w_terms) |
+                       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias);
+  if (al & 15u) return MVD_ERR_MISALIGNED;
+  const int Ho = (Hi + 2 - 3) / stride + 1, Wo = (Wi + 2 - 3) / stride + 1;
+  if ((int64_t)NB * Ho * Wo > 0x7fffffffLL) return MVD_ERR_BAD_SHAPE;
+  // tile = TY x TX output pixels, TX the largest divisor of Wo that fits 128 rows (a TMA box cannot wrap image rows)
+  int TX = 0;
+  for (int d = (Wo < kBM ? Wo : kBM); d >= 1; --d)
+    if (Wo % d == 0) {
+      TX = d;
+      break;
+    }
+  if (TX < 16) return MVD_ERR_UNSUPPORTED;  // e.g. a prime width above 128: the caller keeps the im2col route
+  int TY = kBM / TX;
+  if (TY > Ho) TY = Ho;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return MVD_ERR_NO_DEVICE;
+  alignas(64) CUtensorMap tm_a, tm_b;
+  {  // to load n elements with traversal stride s the box spans n * s (cuTensorMapEncodeTiled: ceil(box / stride) loaded)
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)NB};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)Wi * C * 4, (cuuint64_t)Hi * Wi * C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(TX * stride), (cuuint32_t)(TY * stride), 1u};
+    const cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+    if (box[1] > 256u || box[2] > 256u) return MVD_ERR_UNSUPPORTED;
+    if (enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(src), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return MVD_ERR_UNSUPPORTED;
+  }
+  const int K = 9 * C;
+  if (int e = encode_w_terms(&tm_b, w_terms, K, N, terms)) return e;
+  GbParams prm = {};
+  prm.bias = bias;
+  prm.out = out;
+  prm.rows = NB * Ho * Wo;
+  prm.K = K;
+  prm.N = N;
+  prm.relu = relu;
+  prm.conv = 1;
+  prm.cHo = Ho;
+  prm.cWo = Wo;
+  prm.TX = TX;
+  prm.TY = TY;
+  prm.tiles_x = Wo / TX;
+  prm.tiles_y = (Ho + TY - 1) / TY;
+  prm.cchunks = C / kBK;
+  prm.cstride = stride;
+  prm.m_blocks = NB * prm.tiles_x * prm.tiles_y;
+  prm.n_tiles = (int)ceil_div64(N, kBN);
+  prm.multicast = multicast;
+  return launch_ts(tm_a, tm_b, prm, terms, stream);
 }
 
 extern "C" int mvd_linear_bf16x3_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K, int N,
@@ -857,6 +958,13 @@ extern "C" int mvd_linear_f16x2_f32(const float* x, const void* w_terms, const f
 extern "C" int mvd_linear_f16x2_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows, int K,
                                               int N, int relu, float* out_mc, void* stream) {
   return linear_bf16x3(x, w_terms, bias, rows, K, N, relu, out_mc, 1, 1, stream, 2);
+}
+
+// terms = 2: w_terms from mvd_f16_split2_f32 (default); terms = 3: from mvd_bf16_split3_f32. The weight matrix is
+// [N][9 C] with columns ordered (ky, kx, c).
+extern "C" int mvd_conv3x3_nhwc_f32(const float* src, const void* w_terms, const float* bias, int NB, int Hi, int Wi,
+                                    int C, int stride, int N, int relu, int terms, float* out, void* stream) {
+  return conv3x3_nhwc(src, w_terms, bias, NB, Hi, Wi, C, stride, N, relu, terms, out, 0, stream);
 }
 
 extern "C" int mvd_linear_bf16x3_ts_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows,

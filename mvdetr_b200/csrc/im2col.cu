@@ -156,9 +156,54 @@ __global__ void __launch_bounds__(kImThreads) upsample_im2col_kernel(const float
   }
 }
 
+// Plain bilinear upsample (align_corners = false, ATen arithmetic as above) of a channels-last map, rows [row0, row0 +
+// nrows) of the output only: the input side of the implicit-GEMM 3x3 convolution (csrc/gemm_bf16x3.cu), which fetches
+// its taps by TMA instead of reading an im2col matrix. One thread = one pixel x 4 channels.
+__global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restrict__ src, int C, int Hi, int Wi, int Ho,
+                                                            int Wo, float scale_h, float scale_w, int row0, int nrows,
+                                                            float* __restrict__ dst) {
+  const int n = blockIdx.y;
+  const int c4 = C / 4;
+  const int64_t total = (int64_t)nrows * Wo * c4;
+  const float* sbase = src + (int64_t)n * Hi * Wi * C;
+  float* dbase = dst + (int64_t)n * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) * 4;
+    const int64_t p = i / c4;
+    const int v = (int)(p / Wo) + row0, u = (int)(p % Wo);
+    const UpTap ty = up_tap(v, scale_h, Hi), tx = up_tap(u, scale_w, Wi);
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i0 * Wi + tx.i0) * C + c));
+    const float4 v01 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i0 * Wi + tx.i1) * C + c));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i1 * Wi + tx.i0) * C + c));
+    const float4 v11 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i1 * Wi + tx.i1) * C + c));
+    float4 acc;
+    acc.x = ty.l0 * (tx.l0 * v00.x + tx.l1 * v01.x) + ty.l1 * (tx.l0 * v10.x + tx.l1 * v11.x);
+    acc.y = ty.l0 * (tx.l0 * v00.y + tx.l1 * v01.y) + ty.l1 * (tx.l0 * v10.y + tx.l1 * v11.y);
+    acc.z = ty.l0 * (tx.l0 * v00.z + tx.l1 * v01.z) + ty.l1 * (tx.l0 * v10.z + tx.l1 * v11.z);
+    acc.w = ty.l0 * (tx.l0 * v00.w + tx.l1 * v01.w) + ty.l1 * (tx.l0 * v10.w + tx.l1 * v11.w);
+    *reinterpret_cast<float4*>(dbase + ((int64_t)v * Wo + u) * C + c) = acc;
+  }
+}
+
 }  // namespace mvd
 
 using namespace mvd;
+
+extern "C" int mvd_upsample_nhwc_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, int row0, int nrows,
+                                     float* dst, void* stream) {
+  if (!src || !dst) return MVD_ERR_NULL_POINTER;
+  if (BN <= 0 || C <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0 || BN > 65535) return MVD_ERR_BAD_SHAPE;
+  if (row0 < 0 || nrows <= 0 || row0 + nrows > Ho) return MVD_ERR_BAD_SHAPE;
+  if (C % 4 != 0) return MVD_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) return MVD_ERR_MISALIGNED;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;  // ATen area_pixel_compute_scale
+  const int64_t total = (int64_t)nrows * Wo * (C / 4);
+  const int64_t want = ceil_div64(total, 256);
+  dim3 grid((unsigned)(want > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : want), (unsigned)BN);
+  upsample_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, Hi, Wi, Ho, Wo, sh, sw, row0, nrows, dst);
+  MVD_LAUNCH_CHECK();
+  return MVD_OK;
+}
 
 extern "C" int mvd_warp_im2col_f32(const float* src, const float* Mat, int BN, int C, int Hi, int Wi, int Ho, int Wo,
                                    int stride, float* A, void* stream) {

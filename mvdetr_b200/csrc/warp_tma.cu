@@ -42,15 +42,6 @@ struct WtParams {
   int Ho2, Wo2;  // im2col: token grid
 };
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
-      "[%6];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
-
 // MODE: destination layout. TH x TW = kWtThreads destination pixels per block. S: convolution stride (im2col only).
 template <int MODE, int TH, int TW, int S>
 __global__ void __launch_bounds__(kWtThreads, 2)

@@ -545,6 +545,65 @@ def linear(x, weight, bias=None, relu=False, mode=None, out=None):
     return torch.relu_(res) if relu else res
 
 
+# "implicit": the 3x3 convolutions of the fast path fetch their taps by TMA from the channels-last map (no im2col matrix);
+# "im2col": round-1/2 route (warp / upsample kernels write the im2col matrix, one Linear GEMM reads it). Same results.
+_CONV_MODE = os.environ.get("MVDETR_B200_CONV3X3", "implicit")
+
+
+def conv3x3_implicit_ok(c_in, n_out):
+    """True when the fast path should try conv3x3_nhwc: own split-operand kernel with the x terms in tensor memory selected,
+    32-channel chunks. (An output width without a divisor in [16, 128] is reported by the library: conv3x3_nhwc -> None.)"""
+    return (_CONV_MODE == "implicit" and (_GEMM_MODE == "f16x2" or (_GEMM_MODE == "bf16x3" and _GEMM_TS)) and
+            c_in % 32 == 0 and n_out % 4 == 0)
+
+
+def conv3x3_nhwc(x_cl, w2d, bias=None, stride=1, relu=False):
+    """3x3 / pad 1 / stride convolution of x_cl [NB,Hi,Wi,C] (channels-last storage, fp32 CUDA) with the weight matrix
+    w2d [N, 9*C] whose columns are ordered (ky, kx, c) -> [NB*Ho*Wo, N] (channels-last rows), as an implicit GEMM on
+    our tcgen05 kernel (mvd_conv3x3_nhwc_f32). Bit-identical to linear(im2col(x), w2d). Returns None when the library
+    reports the shape unsupported (callers keep the im2col route)."""
+    NB, Hi, Wi, C = x_cl.shape
+    N = w2d.shape[0]
+    if w2d.shape[1] != 9 * C:
+        raise RuntimeError("conv3x3_nhwc: weight matrix must be [N, 9*C] with (ky, kx, c) columns")
+    for name, t in (("x", x_cl), ("weight", w2d), ("bias", bias)):
+        if t is not None and not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError(f"conv3x3_nhwc: {name} must be a contiguous fp32 CUDA tensor")
+    Ho, Wo = (Hi - 1) // stride + 1, (Wi - 1) // stride + 1
+    if _GEMM_MODE == "f16x2":
+        terms, nt = _f16_split2(w2d), 2
+    else:
+        terms, nt = _bf16_split3(w2d), 3
+    out = torch.empty((NB * Ho * Wo, N), dtype=x_cl.dtype, device=x_cl.device)
+    with _on_device(x_cl):
+        rc = _C.lib.mvd_conv3x3_nhwc_f32(x_cl.data_ptr(), terms.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                         NB, Hi, Wi, C, int(stride), N, 1 if relu else 0, nt, out.data_ptr(),
+                                         _stream(x_cl))
+    if rc == -3:
+        return None
+    _C.check(rc, "mvd_conv3x3_nhwc_f32")
+    return out
+
+
+def upsample_nhwc(x_cl, dsize, rows=None, out=None):
+    """Bilinear upsample (align_corners=False, ATen arithmetic) of x_cl [BN,Hi,Wi,C] channels-last fp32 CUDA to
+    [BN,Ho,Wo,C]; rows=(row0, nrows) writes only that band of output rows into `out` (the rest is left untouched)."""
+    BN, Hi, Wi, C = x_cl.shape
+    Ho, Wo = int(dsize[0]), int(dsize[1])
+    if not (x_cl.is_cuda and x_cl.is_contiguous() and x_cl.dtype == torch.float32 and C % 4 == 0):
+        raise RuntimeError("upsample_nhwc: contiguous fp32 CUDA [BN,Hi,Wi,C] with C % 4 == 0 required")
+    row0, nrows = (0, Ho) if rows is None else (int(rows[0]), int(rows[1]))
+    if out is None:
+        out = torch.empty((BN, Ho, Wo, C), dtype=x_cl.dtype, device=x_cl.device)
+    elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (BN, Ho, Wo, C)):
+        raise RuntimeError("upsample_nhwc: out must be a contiguous fp32 CUDA [BN,Ho,Wo,C]")
+    with _on_device(x_cl):
+        rc = _C.lib.mvd_upsample_nhwc_f32(x_cl.data_ptr(), BN, C, Hi, Wi, Ho, Wo, row0, nrows, out.data_ptr(),
+                                          _stream(x_cl))
+    _C.check(rc, "mvd_upsample_nhwc_f32")
+    return out
+
+
 def linear_multicast(x, weight, bias, mc_ptr, relu=False):
     """act(x @ weight.T + bias) written through the NVLink MULTICAST address `mc_ptr` (int; the slot of a symmetric buffer
     as mapped by torch.distributed._symmetric_memory): the GEMM's epilogue is the all-gather -- every 16-byte piece

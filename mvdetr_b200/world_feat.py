@@ -320,6 +320,12 @@ class DeformTransWorldFeat(nn.Module):
                 self.hidden_dim % 4 == 0 and x.shape[1] % 4 == 0 and self.stride == 2 and
                 self.encoder.ref_table is not None)
 
+    def tokens_from_warped(self, g_cl):
+        """g_cl [N, Hg, Wg, C_in] channels-last warped grid -> downsample conv (3x3, stride 2) + ReLU as an implicit GEMM
+        (no im2col matrix) -> [tokens, hidden], or None when the library cannot take the shape."""
+        Wd, _, _ = self.gemm_weights()
+        return ops.conv3x3_nhwc(g_cl, Wd, self.downsample[0].bias, stride=2, relu=True)
+
     def tokens_from_im2col(self, A):
         """A [tokens, 9*C_in] (ops.warp_im2col) -> downsample conv + ReLU as one GEMM -> [tokens, hidden]."""
         Wd, _, _ = self.gemm_weights()
@@ -344,9 +350,20 @@ class DeformTransWorldFeat(nn.Module):
         C = self.hidden_dim
         Hg, Wg = self.Rworld_shape
         merged = ops.linear(mem_cm, Wm, self.merge_linear[0].bias, relu=True)            # [cells, C] = NHWC map
-        A = ops.upsample_im2col(merged.view(1, Hd, Wd, C), (Hg, Wg))                      # [Hg*Wg, 9C]
-        out_cl = ops.linear(A, Wu, self.upsample[1].bias, relu=True)                     # [Hg*Wg, C]
+        out_cl = None
+        if ops.conv3x3_implicit_ok(C, Wu.shape[0]):  # upsample -> implicit-GEMM conv: no [Hg*Wg, 9C] matrix
+            up = ops.upsample_nhwc(merged.view(1, Hd, Wd, C), (Hg, Wg))
+            out_cl = ops.conv3x3_nhwc(up, Wu, self.upsample[1].bias, stride=1, relu=True)
+        if out_cl is None:
+            A = ops.upsample_im2col(merged.view(1, Hd, Wd, C), (Hg, Wg))                  # [Hg*Wg, 9C]
+            out_cl = ops.linear(A, Wu, self.upsample[1].bias, relu=True)                 # [Hg*Wg, C]
         return ops.transpose_last2(out_cl.view(1, Hg * Wg, C)).view(1, C, Hg, Wg)
+
+    def forward_from_tokens(self, tokens, N, Hd, Wd):
+        """Whole stage from the downsample conv's output tokens [N*Hd*Wd, hidden] (B = 1): -> [1, hidden, Hg, Wg]."""
+        src = tokens.view(1, N * Hd * Wd, self.hidden_dim)
+        mem_cm = self.encode_tokens(src, N, Hd, Wd, perm_inner_last=Hd * Wd)
+        return self.tail_from_cell_major(mem_cm.view(Hd * Wd, N * self.hidden_dim), Hd, Wd)
 
     def forward_from_im2col(self, A, N, Hd, Wd):
         """Whole stage from the warp's im2col matrix (B = 1, as the reference): -> [1, hidden, Hg, Wg]."""

@@ -109,3 +109,62 @@ def test_f16x2_range_contract(cuda):
     ok = ops.linear(big, w, None, mode="bf16x3")
     assert torch.isfinite(ok).all()
     assert (ok.double() - big.double() @ w.double().t()).abs().max().item() <= 1e-6 * 1e6
+
+
+@pytest.mark.parametrize("NB,Hi,Wi,C,N,stride", [
+    (7, 120, 360, 128, 128, 2),    # Wildtrack downsample conv: tile 2 x 60 output pixels
+    (1, 120, 360, 128, 128, 1),    # Wildtrack upsample conv: tile 1 x 120
+    (6, 160, 250, 128, 128, 2),    # MultiviewX: output width 125 = one tile row
+    (2, 37, 64, 32, 20, 1),        # partial tiles in y (TY = 2 over 37 rows), narrow N, one channel chunk
+    (3, 33, 48, 64, 132, 2),       # odd input height, two column tiles
+])
+def test_implicit_conv3x3_is_the_im2col_gemm_bit_for_bit(cuda, NB, Hi, Wi, C, N, stride):
+    """The implicit-GEMM convolution (taps fetched by TMA from the channels-last image, zero padding = TMA out-of-bounds
+    fill) against F.conv2d in fp64, and bit for bit against the same kernel fed the materialised (ky, kx, c) im2col matrix."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(NB * 1000 + Hi)
+    x = torch.randn(NB, C, Hi, Wi, generator=g).to(cuda)
+    w = (torch.randn(N, C, 3, 3, generator=g) / (9 * C) ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g).to(cuda)
+    x_cl = x.permute(0, 2, 3, 1).contiguous()
+    w2d = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    for mode in ("f16x2", "bf16x3"):
+        old = ops._GEMM_MODE
+        ops._GEMM_MODE = mode
+        try:
+            got = ops.conv3x3_nhwc(x_cl, w2d, b, stride=stride, relu=True)
+        finally:
+            ops._GEMM_MODE = old
+        assert got is not None
+        Ho, Wo = (Hi - 1) // stride + 1, (Wi - 1) // stride + 1
+        exact = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=1).clamp_min(0)
+        exact = exact.permute(0, 2, 3, 1).reshape(NB * Ho * Wo, N)
+        ref32 = F.conv2d(x, w, b, stride=stride, padding=1).clamp_min(0).permute(0, 2, 3, 1).reshape(NB * Ho * Wo, N)
+        err, err32 = (got.double() - exact).abs().max().item(), (ref32.double() - exact).abs().max().item()
+        assert err <= max(4 * err32, 4e-6 * exact.abs().max().item()), (mode, err, err32)
+        # materialised im2col matrix, columns (ky, kx, c): unfold gives (c, ky, kx) -> reorder
+        cols = F.unfold(x, 3, padding=1, stride=stride).view(NB, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(NB * Ho * Wo, 9 * C)
+        via_matrix = ops.linear(cols.contiguous(), w2d, b, relu=True, mode=mode)
+        assert torch.equal(got, via_matrix), mode
+
+
+def test_implicit_conv3x3_reports_unsupported_widths(cuda):
+    x_cl = torch.randn(1, 8, 131, 32, device=cuda)   # output width 131 is prime and > 128: no tile width
+    w2d = torch.randn(16, 9 * 32, device=cuda)
+    assert ops.conv3x3_nhwc(x_cl, w2d, None, stride=1) is None
+
+
+def test_upsample_nhwc_matches_aten(cuda):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 128, 60, 180, generator=g).to(cuda)
+    x_cl = x.permute(0, 2, 3, 1).contiguous()
+    ref = F.interpolate(x, size=(120, 360), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    got = ops.upsample_nhwc(x_cl, (120, 360))
+    assert (got - ref).abs().max().item() <= 1e-6
+    band = torch.zeros_like(got)
+    ops.upsample_nhwc(x_cl, (120, 360), rows=(17, 40), out=band)
+    assert torch.equal(band[:, 17:57], got[:, 17:57]) and band[:, :17].abs().max().item() == 0 and band[:, 57:].abs().max().item() == 0
+    # same arithmetic as the im2col variant's centre tap
+    A = ops.upsample_im2col(x_cl[:1].contiguous(), (120, 360))
+    assert torch.equal(A.view(120, 360, 9, 128)[:, :, 4], got[0])
