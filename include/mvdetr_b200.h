@@ -363,9 +363,12 @@ MVD_API int mvd_multicast_copy_f32(const float* src, float* dst_mc, int64_t rows
  * (ref: multiview_detector/models/trans_world_feat.py:74,82-84,89,109). MVD_ERR_UNSUPPORTED when the output width has
  * no divisor in [16, 128] (callers keep the im2col route).
  * mvd_upsample_nhwc_f32: bilinear upsample (align_corners = false, ATen arithmetic) of a channels-last map, output rows
- * [row0, row0 + nrows) only: the input of that convolution (ref: trans_world_feat.py:83 nn.Upsample). */
+ * [row0, row0 + nrows) only: the input of that convolution (ref: trans_world_feat.py:83 nn.Upsample).
+ * addend / out2 (both or neither, [NB * Ho * Wo][N]): out2 = out + addend from the same epilogue -- the first encoder
+ * layer's query `src + pos` (ref: multiview_detector/models/deformable_transformer.py:71-77) without a kernel of its own. */
 MVD_API int mvd_conv3x3_nhwc_f32(const float* src, const void* w_terms, const float* bias, int NB, int Hi, int Wi, int C,
-                         int stride, int N, int relu, int terms, float* out, void* stream);
+                         int stride, int N, int relu, int terms, float* out, const float* addend, float* out2,
+                         void* stream);
 MVD_API int mvd_upsample_nhwc_f32(const float* src, int BN, int C, int Hi, int Wi, int Ho, int Wo, int row0, int nrows,
                           float* dst, void* stream);
 /* Same two GEMMs (same arguments, bit-identical results) with the three bf16 terms of x staged in TENSOR MEMORY by the

@@ -46,7 +46,7 @@ SIGNATURES = {
     "mvd_bf16_split3_f32": [_p, ctypes.c_int64, _p, _p],
     "mvd_linear_bf16x3_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
     "mvd_linear_bf16x3_multicast_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],
-    "mvd_conv3x3_nhwc_f32": [_p, _p, _p] + [_i] * 8 + [_p, _p],
+    "mvd_conv3x3_nhwc_f32": [_p, _p, _p] + [_i] * 8 + [_p, _p, _p, _p],
     "mvd_upsample_nhwc_f32": [_p] + [_i] * 8 + [_p, _p],
     "mvd_f16_split2_f32": [_p, ctypes.c_int64, _p, _p],
     "mvd_linear_f16x2_f32": [_p, _p, _p, ctypes.c_int64, _i, _i, _i, _p, _p],

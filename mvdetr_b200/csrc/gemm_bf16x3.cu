@@ -63,6 +63,10 @@ struct GbParams {
   // convolution over it (K = 9 C, taps (ky, kx, c)): a row block is a TY x TX tile of output pixels of one image and a K
   // chunk is 32 channels of one tap, fetched by TMA straight from the image (no im2col matrix in memory)
   int conv, cHo, cWo, TX, TY, tiles_x, tiles_y, cchunks, cstride;
+  // TS kernels, optional second output: out2 = out + addend (same [rows, N] layout): the first encoder layer's query
+  // `src + pos` leaves the downsample convolution's epilogue instead of an element-wise kernel of its own
+  const float* addend;
+  float* out2;
 };
 
 __device__ __forceinline__ void tma_load_2d_b(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -728,6 +732,11 @@ __global__ void __launch_bounds__(kTsThreads, 1)
                                : "memory");
                 else
                   *reinterpret_cast<float4*>(dst) = x;
+                if (prm.out2) {
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(prm.addend + grow[i] * prm.N + n));
+                  *reinterpret_cast<float4*>(prm.out2 + grow[i] * prm.N + n) =
+                      make_float4(x.x + a.x, x.y + a.y, x.z + a.z, x.w + a.w);
+                }
               }
             }
           }
@@ -871,8 +880,10 @@ static int linear_bf16x3(const float* x, const void* w_terms, const float* bias,
 // matrix. Output [NB * Ho * Wo, N] (channels-last). Bit-identical to mvd_linear_* over the (ky, kx, c)-ordered im2col
 // matrix of the same image: the K chunks, their order and the accumulators are the same.
 static int conv3x3_nhwc(const float* src, const void* w_terms, const float* bias, int NB, int Hi, int Wi, int C,
-                        int stride, int N, int relu, int terms, float* out, int multicast, void* stream) {
-  if (!src || !w_terms || !out) return MVD_ERR_NULL_POINTER;
+                        int stride, int N, int relu, int terms, float* out, const float* addend, float* out2,
+                        int multicast, void* stream) {
+  if (!src || !w_terms || !out || ((addend == nullptr) != (out2 == nullptr))) return MVD_ERR_NULL_POINTER;
+  if ((reinterpret_cast<uintptr_t>(addend) | reinterpret_cast<uintptr_t>(out2)) & 15u) return MVD_ERR_MISALIGNED;
   if (NB <= 0 || Hi <= 0 || Wi <= 0 || C <= 0 || N <= 0) return MVD_ERR_BAD_SHAPE;
   if ((stride != 1 && stride != 2) || (terms != 2 && terms != 3)) return MVD_ERR_BAD_SHAPE;
   if (C % kBK != 0 || N % 4 != 0) return MVD_ERR_UNSUPPORTED;  // a K chunk is 32 channels of one tap
@@ -926,6 +937,8 @@ static int conv3x3_nhwc(const float* src, const void* w_terms, const float* bias
   prm.m_blocks = NB * prm.tiles_x * prm.tiles_y;
   prm.n_tiles = (int)ceil_div64(N, kBN);
   prm.multicast = multicast;
+  prm.addend = addend;
+  prm.out2 = out2;
   return launch_ts(tm_a, tm_b, prm, terms, stream);
 }
 
@@ -963,8 +976,9 @@ extern "C" int mvd_linear_f16x2_multicast_f32(const float* x, const void* w_term
 // terms = 2: w_terms from mvd_f16_split2_f32 (default); terms = 3: from mvd_bf16_split3_f32. The weight matrix is
 // [N][9 C] with columns ordered (ky, kx, c).
 extern "C" int mvd_conv3x3_nhwc_f32(const float* src, const void* w_terms, const float* bias, int NB, int Hi, int Wi,
-                                    int C, int stride, int N, int relu, int terms, float* out, void* stream) {
-  return conv3x3_nhwc(src, w_terms, bias, NB, Hi, Wi, C, stride, N, relu, terms, out, 0, stream);
+                                    int C, int stride, int N, int relu, int terms, float* out, const float* addend,
+                                    float* out2, void* stream) {
+  return conv3x3_nhwc(src, w_terms, bias, NB, Hi, Wi, C, stride, N, relu, terms, out, addend, out2, 0, stream);
 }
 
 extern "C" int mvd_linear_bf16x3_ts_multicast_f32(const float* x, const void* w_terms, const float* bias, int64_t rows,

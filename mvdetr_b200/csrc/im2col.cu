@@ -118,6 +118,20 @@ __device__ __forceinline__ UpTap up_tap(int dst, float scale, int in_size) {
   return t;
 }
 
+// ATen: h0lambda * (w0lambda * v00 + w1lambda * v01) + h1lambda * (w0lambda * v10 + w1lambda * v11). The operation
+// sequence is pinned with intrinsics so that the two kernels below give the same bits (left to the compiler, the im2col
+// and the plain kernel contracted different multiply-adds: r02t).
+__device__ __forceinline__ float up_blend1(const UpTap& ty, const UpTap& tx, float v00, float v01, float v10, float v11) {
+  const float top = __fmaf_rn(tx.l1, v01, __fmul_rn(tx.l0, v00));
+  const float bot = __fmaf_rn(tx.l1, v11, __fmul_rn(tx.l0, v10));
+  return __fmaf_rn(ty.l1, bot, __fmul_rn(ty.l0, top));
+}
+__device__ __forceinline__ float4 up_blend(const UpTap& ty, const UpTap& tx, const float4& v00, const float4& v01,
+                                           const float4& v10, const float4& v11) {
+  return make_float4(up_blend1(ty, tx, v00.x, v01.x, v10.x, v11.x), up_blend1(ty, tx, v00.y, v01.y, v10.y, v11.y),
+                     up_blend1(ty, tx, v00.z, v01.z, v10.z, v11.z), up_blend1(ty, tx, v00.w, v01.w, v10.w, v11.w));
+}
+
 // Rows [row0, row0 + nrows) of the upsampled grid only (nrows = Ho, row0 = 0: the whole grid): the block index walks
 // the padded pixel rows [row0 - 1, row0 + nrows] that feed those tokens.
 __global__ void __launch_bounds__(kImThreads) upsample_im2col_kernel(const float* __restrict__ src, int C, int Hi,
@@ -145,11 +159,7 @@ __global__ void __launch_bounds__(kImThreads) upsample_im2col_kernel(const float
         const float4 v01 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i0 * Wi + tx.i1) * C + c));
         const float4 v10 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i1 * Wi + tx.i0) * C + c));
         const float4 v11 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i1 * Wi + tx.i1) * C + c));
-        // ATen: h0lambda * (w0lambda * v00 + w1lambda * v01) + h1lambda * (w0lambda * v10 + w1lambda * v11)
-        acc.x = ty.l0 * (tx.l0 * v00.x + tx.l1 * v01.x) + ty.l1 * (tx.l0 * v10.x + tx.l1 * v11.x);
-        acc.y = ty.l0 * (tx.l0 * v00.y + tx.l1 * v01.y) + ty.l1 * (tx.l0 * v10.y + tx.l1 * v11.y);
-        acc.z = ty.l0 * (tx.l0 * v00.z + tx.l1 * v01.z) + ty.l1 * (tx.l0 * v10.z + tx.l1 * v11.z);
-        acc.w = ty.l0 * (tx.l0 * v00.w + tx.l1 * v01.w) + ty.l1 * (tx.l0 * v10.w + tx.l1 * v11.w);
+        acc = up_blend(ty, tx, v00, v01, v10, v11);
       }
       scatter_slots(A, acc, vp, up, c, C, 1, Ho, Wo, token0, row0, row0 + nrows);
     }
@@ -176,11 +186,7 @@ __global__ void __launch_bounds__(256) upsample_nhwc_kernel(const float* __restr
     const float4 v01 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i0 * Wi + tx.i1) * C + c));
     const float4 v10 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i1 * Wi + tx.i0) * C + c));
     const float4 v11 = __ldg(reinterpret_cast<const float4*>(sbase + ((int64_t)ty.i1 * Wi + tx.i1) * C + c));
-    float4 acc;
-    acc.x = ty.l0 * (tx.l0 * v00.x + tx.l1 * v01.x) + ty.l1 * (tx.l0 * v10.x + tx.l1 * v11.x);
-    acc.y = ty.l0 * (tx.l0 * v00.y + tx.l1 * v01.y) + ty.l1 * (tx.l0 * v10.y + tx.l1 * v11.y);
-    acc.z = ty.l0 * (tx.l0 * v00.z + tx.l1 * v01.z) + ty.l1 * (tx.l0 * v10.z + tx.l1 * v11.z);
-    acc.w = ty.l0 * (tx.l0 * v00.w + tx.l1 * v01.w) + ty.l1 * (tx.l0 * v10.w + tx.l1 * v11.w);
+    const float4 acc = up_blend(ty, tx, v00, v01, v10, v11);
     *reinterpret_cast<float4*>(dbase + ((int64_t)v * Wo + u) * C + c) = acc;
   }
 }

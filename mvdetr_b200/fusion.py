@@ -50,9 +50,10 @@ class MultiviewFusion(nn.Module):
             # NCHW source), downsample conv as an IMPLICIT GEMM fetching its taps by TMA -- no im2col matrix in memory
             if ops.conv3x3_implicit_ok(C, self.world_feat.hidden_dim):
                 g_cl = ops.warp_perspective(imgs_feat, proj_mats, (Hg, Wg), align_corners=False, channels_last=True)
-                tokens = self.world_feat.tokens_from_warped(g_cl)
-                if tokens is not None:
-                    return self.world_feat.forward_from_tokens(tokens, self.num_cam, (Hg - 1) // 2 + 1, (Wg - 1) // 2 + 1)
+                res = self.world_feat.tokens_from_warped(g_cl, with_query=True)
+                if res is not None:
+                    return self.world_feat.forward_from_tokens(res[0], self.num_cam, (Hg - 1) // 2 + 1,
+                                                               (Wg - 1) // 2 + 1, query0=res[1])
             # im2col route: warp straight into the downsample conv's im2col matrix
             A, (Hd, Wd) = ops.warp_im2col(imgs_feat, proj_mats, (Hg, Wg), stride=2)
             return self.world_feat.forward_from_im2col(A, self.num_cam, Hd, Wd)

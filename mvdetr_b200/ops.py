@@ -557,11 +557,12 @@ def conv3x3_implicit_ok(c_in, n_out):
             c_in % 32 == 0 and n_out % 4 == 0)
 
 
-def conv3x3_nhwc(x_cl, w2d, bias=None, stride=1, relu=False):
+def conv3x3_nhwc(x_cl, w2d, bias=None, stride=1, relu=False, add=None):
     """3x3 / pad 1 / stride convolution of x_cl [NB,Hi,Wi,C] (channels-last storage, fp32 CUDA) with the weight matrix
     w2d [N, 9*C] whose columns are ordered (ky, kx, c) -> [NB*Ho*Wo, N] (channels-last rows), as an implicit GEMM on
     our tcgen05 kernel (mvd_conv3x3_nhwc_f32). Bit-identical to linear(im2col(x), w2d). Returns None when the library
-    reports the shape unsupported (callers keep the im2col route)."""
+    reports the shape unsupported (callers keep the im2col route). add [NB*Ho*Wo, N] (or broadcastable view of that
+    element count): returns (out, out + add), the sum written by the same epilogue."""
     NB, Hi, Wi, C = x_cl.shape
     N = w2d.shape[0]
     if w2d.shape[1] != 9 * C:
@@ -575,14 +576,20 @@ def conv3x3_nhwc(x_cl, w2d, bias=None, stride=1, relu=False):
     else:
         terms, nt = _bf16_split3(w2d), 3
     out = torch.empty((NB * Ho * Wo, N), dtype=x_cl.dtype, device=x_cl.device)
+    out2 = None
+    if add is not None:
+        if not (add.is_cuda and add.is_contiguous() and add.dtype == torch.float32 and add.numel() == out.numel()):
+            raise RuntimeError("conv3x3_nhwc: add must be a contiguous fp32 CUDA tensor with the output's element count")
+        out2 = torch.empty_like(out)
     with _on_device(x_cl):
         rc = _C.lib.mvd_conv3x3_nhwc_f32(x_cl.data_ptr(), terms.data_ptr(), bias.data_ptr() if bias is not None else None,
                                          NB, Hi, Wi, C, int(stride), N, 1 if relu else 0, nt, out.data_ptr(),
-                                         _stream(x_cl))
+                                         add.data_ptr() if add is not None else None,
+                                         out2.data_ptr() if out2 is not None else None, _stream(x_cl))
     if rc == -3:
         return None
     _C.check(rc, "mvd_conv3x3_nhwc_f32")
-    return out
+    return out if add is None else (out, out2)
 
 
 def upsample_nhwc(x_cl, dsize, rows=None, out=None):

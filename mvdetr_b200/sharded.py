@@ -152,6 +152,11 @@ class ShardedFusion:
             Hd, Wd = wf.pos_embedding.shape[-2:]
             return feat_local.new_zeros((0, C)), Hd, Wd
         if self.fusion.gemm_path and wf.fast_path_ok(feat_local):
+            if ops.conv3x3_implicit_ok(feat_local.shape[1], C):  # same route (and bits) as the single-GPU frame
+                g_cl = ops.warp_perspective(feat_local, proj_local, (Hg, Wg), align_corners=False, channels_last=True)
+                t = wf.tokens_from_warped(g_cl)
+                if t is not None:
+                    return t, (Hg - 1) // 2 + 1, (Wg - 1) // 2 + 1
             A, (Hd, Wd) = ops.warp_im2col(feat_local, proj_local, (Hg, Wg), stride=2)
             return wf.tokens_from_im2col(A), Hd, Wd
         world = ops.warp_perspective(feat_local, proj_local, (Hg, Wg), align_corners=False, channels_last=True)

@@ -246,14 +246,14 @@ class DeformableTransformerEncoder(nn.Module):
         return torch.cat(per_level, 1)[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
-                geometry=None, perm_inner_last=0):
+                geometry=None, perm_inner_last=0, query0=None):
         output = src
         if self.reference_points is None:
             hw = geometry.hw if geometry is not None else spatial_shapes.tolist()
             reference_points = self.get_reference_points(hw, valid_ratios, device=src.device)
         else:
             reference_points = self.reference_points.unsqueeze(0).expand(src.shape[0], -1, -1, -1, -1)
-        query = None
+        query = query0  # src + pos when the producer of src formed it (fast path), else the layer adds it
         for i, layer in enumerate(self.layers):
             last = i == self.num_layers - 1
             res = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask,
@@ -320,28 +320,40 @@ class DeformTransWorldFeat(nn.Module):
                 self.hidden_dim % 4 == 0 and x.shape[1] % 4 == 0 and self.stride == 2 and
                 self.encoder.ref_table is not None)
 
-    def tokens_from_warped(self, g_cl):
+    def tokens_from_warped(self, g_cl, with_query=False):
         """g_cl [N, Hg, Wg, C_in] channels-last warped grid -> downsample conv (3x3, stride 2) + ReLU as an implicit GEMM
-        (no im2col matrix) -> [tokens, hidden], or None when the library cannot take the shape."""
+        (no im2col matrix) -> [tokens, hidden], or None when the library cannot take the shape. with_query: returns
+        (tokens, tokens + pos): the first encoder layer's query leaves the same epilogue."""
         Wd, _, _ = self.gemm_weights()
-        return ops.conv3x3_nhwc(g_cl, Wd, self.downsample[0].bias, stride=2, relu=True)
+        if not with_query:
+            return ops.conv3x3_nhwc(g_cl, Wd, self.downsample[0].bias, stride=2, relu=True)
+        N, Hg, Wg = g_cl.shape[0], g_cl.shape[1], g_cl.shape[2]
+        pos = self._pos_rows(1, N, (Hg - 1) // 2 + 1, (Wg - 1) // 2 + 1)
+        return ops.conv3x3_nhwc(g_cl, Wd, self.downsample[0].bias, stride=2, relu=True, add=pos)
+
+    def _pos_rows(self, B, N, Hd, Wd):
+        """Position + level embedding rows [B, N*Hd*Wd, C] (static at inference; cached per embedding version)."""
+        C = self.hidden_dim
+        key = (id(self.lvl_embedding), self.lvl_embedding._version, id(self.pos_embedding), self.pos_embedding.device)
+        if getattr(self, "_pos_key", None) != key:
+            self._pos = (self.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
+                         self.lvl_embedding.detach().view([B, N, 1, C])).view([B, N * Hd * Wd, C]).contiguous()
+            self._pos_key = key
+        return self._pos
 
     def tokens_from_im2col(self, A):
         """A [tokens, 9*C_in] (ops.warp_im2col) -> downsample conv + ReLU as one GEMM -> [tokens, hidden]."""
         Wd, _, _ = self.gemm_weights()
         return ops.linear(A, Wd, self.downsample[0].bias, relu=True)
 
-    def encode_tokens(self, src, N, Hd, Wd, perm_inner_last=0):
-        """src [1, N*Hd*Wd, hidden] view-major tokens -> encoder output (cell-major rows when perm_inner_last)."""
+    def encode_tokens(self, src, N, Hd, Wd, perm_inner_last=0, query0=None):
+        """src [1, N*Hd*Wd, hidden] view-major tokens -> encoder output (cell-major rows when perm_inner_last). query0:
+        src + pos when the producer of src already formed it."""
         B, _, C = src.shape
-        key = (id(self.lvl_embedding), self.lvl_embedding._version, id(self.pos_embedding), self.pos_embedding.device)
-        if getattr(self, "_pos_key", None) != key:  # static at inference: position + level embedding, [1, N*Hd*Wd, C]
-            self._pos = (self.pos_embedding.flatten(2).transpose(1, 2).unsqueeze(1) +
-                         self.lvl_embedding.detach().view([B, N, 1, C])).view([B, N * Hd * Wd, C]).contiguous()
-            self._pos_key = key
-        pos = self._pos
+        pos = self._pos_rows(B, N, Hd, Wd)
         geo = self._level_geometry(N, Hd, Wd, src.device)
-        return self.encoder(src, geo.shapes, geo.start, None, pos, geometry=geo, perm_inner_last=perm_inner_last)
+        return self.encoder(src, geo.shapes, geo.start, None, pos, geometry=geo, perm_inner_last=perm_inner_last,
+                            query0=query0)
 
     def tail_from_cell_major(self, mem_cm, Hd, Wd):
         """mem_cm [Hd*Wd, N*hidden] (row = ground cell, columns = (view, channel)) -> merge 1x1 conv + ReLU, bilinear
@@ -359,10 +371,12 @@ class DeformTransWorldFeat(nn.Module):
             out_cl = ops.linear(A, Wu, self.upsample[1].bias, relu=True)                 # [Hg*Wg, C]
         return ops.transpose_last2(out_cl.view(1, Hg * Wg, C)).view(1, C, Hg, Wg)
 
-    def forward_from_tokens(self, tokens, N, Hd, Wd):
+    def forward_from_tokens(self, tokens, N, Hd, Wd, query0=None):
         """Whole stage from the downsample conv's output tokens [N*Hd*Wd, hidden] (B = 1): -> [1, hidden, Hg, Wg]."""
         src = tokens.view(1, N * Hd * Wd, self.hidden_dim)
-        mem_cm = self.encode_tokens(src, N, Hd, Wd, perm_inner_last=Hd * Wd)
+        if query0 is not None:
+            query0 = query0.view_as(src)
+        mem_cm = self.encode_tokens(src, N, Hd, Wd, perm_inner_last=Hd * Wd, query0=query0)
         return self.tail_from_cell_major(mem_cm.view(Hd * Wd, N * self.hidden_dim), Hd, Wd)
 
     def forward_from_im2col(self, A, N, Hd, Wd):

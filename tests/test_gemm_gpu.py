@@ -146,6 +146,10 @@ def test_implicit_conv3x3_is_the_im2col_gemm_bit_for_bit(cuda, NB, Hi, Wi, C, N,
         cols = F.unfold(x, 3, padding=1, stride=stride).view(NB, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(NB * Ho * Wo, 9 * C)
         via_matrix = ops.linear(cols.contiguous(), w2d, b, relu=True, mode=mode)
         assert torch.equal(got, via_matrix), mode
+    # second output of the same epilogue: out + addend (the first encoder layer's query, src + pos)
+    add = torch.randn(got.shape, generator=g).to(cuda)
+    o1, o2 = ops.conv3x3_nhwc(x_cl, w2d, b, stride=stride, relu=True, add=add)
+    assert torch.equal(o1, ops.conv3x3_nhwc(x_cl, w2d, b, stride=stride, relu=True)) and torch.equal(o2, o1 + add)
 
 
 def test_implicit_conv3x3_reports_unsupported_widths(cuda):
