@@ -352,6 +352,14 @@ def kernel_breakdown(fusion, ds, wl, device, iters=20):
         bb = 4 * (3 * S * HEADS * D + Lq * HEADS * D + 2 * 3 * Lq * HEADS * N * POINTS)
         res["msda_bwd"] = {"us": t, "us_min": tmin, "bytes": bb, "GBps": bb / t / 1e3,
                            "kernel": ops.msda_bwd_kernel_name(value, geo.hw, Lq)}
+        if ops._BWD_BANDED:  # the same kernel walking the pairs in query order (round 1), for comparison
+            ops._BWD_BANDED = False
+            try:
+                t, tmin = time_kernel_events(lambda: ops.ms_deform_attn_backward(value, geo.shapes, geo.start, loc, attn,
+                                                                                 go, 64), max(5, iters // 2), flush)
+            finally:
+                ops._BWD_BANDED = True
+            res["msda_bwd_query_order"] = {"us": t, "us_min": tmin, "GBps": bb / t / 1e3}
         try:  # comparator only; never fatal
             ext = load_ref_ext()
             if ext is not None:

@@ -89,6 +89,15 @@ MVD_API int mvd_msda_bwd_f32(const float* grad_out, const float* value, const in
                      const float* loc, const float* attn,
                      int B, int S, int M, int D, int L, int Lq, int P,
                      float* grad_value, float* grad_loc, float* grad_attn, void* stream);
+/* Same kernels for the MVDeTr encoder layout (L levels of one H x W grid, Lq = R * H * W queries; shapes / start still
+ * describe it): the (query, head) pairs are walked band by band -- (batch, row, view, x, head) -- so the gradient
+ * reductions of concurrently running blocks hit the same few rows of every level and stay in L2 instead of re-fetching
+ * value / grad_value from DRAM once per query view. Results equal mvd_msda_bwd_f32's up to the (unspecified) order of
+ * the fp32 atomic reductions. ref: ms_deform_im2col_cuda.cuh:301-920 (col2im), call site ms_deform_attn_func.py:35. */
+MVD_API int mvd_msda_bwd_banded_f32(const float* grad_out, const float* value, const int64_t* shapes,
+                            const int64_t* start, const float* loc, const float* attn, int B, int S, int M, int D, int L,
+                            int Lq, int P, int H, int W, int R, float* grad_value, float* grad_loc, float* grad_attn,
+                            void* stream);
 MVD_API int mvd_msda_bwd_f64(const double* grad_out, const double* value, const int64_t* shapes, const int64_t* start,
                      const double* loc, const double* attn,
                      int B, int S, int M, int D, int L, int Lq, int P,

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mvd_msda_fwd_f32": [_p] * 5 + [_i] * 7 + [_p, _p],
     "mvd_msda_fwd_f64": [_p] * 5 + [_i] * 7 + [_p, _p],
     "mvd_msda_bwd_f32": [_p] * 6 + [_i] * 7 + [_p] * 4,
+    "mvd_msda_bwd_banded_f32": [_p] * 6 + [_i] * 10 + [_p] * 4,
     "mvd_msda_bwd_f64": [_p] * 6 + [_i] * 7 + [_p] * 4,
     "mvd_msda_fwd_viewgrid_f32": [_p] * 3 + [_i] * 8 + [_p, _p],
     "mvd_msda_bwd_viewgrid_f32": [_p] * 4 + [_i] * 8 + [_p] * 4,

@@ -24,6 +24,7 @@ from . import _C
 
 _VIEWGRID = os.environ.get("MVDETR_B200_VIEWGRID", "1") != "0"
 _BWD_VIEWGRID = os.environ.get("MVDETR_B200_BWD_VIEWGRID", "0") == "1"  # experimental TMA-staged backward (opt-in)
+_BWD_BANDED = os.environ.get("MVDETR_B200_BWD_BANDED", "1") == "1"  # encoder layout: band-by-band pair order in the backward
 _WARP_CL = os.environ.get("MVDETR_B200_WARP_CL", "1") != "0"  # 0: always the scalar NCHW-source warp kernels (A/B switch)
 _WARP_TMA = os.environ.get("MVDETR_B200_WARP_TMA", "1") != "0"  # 0: relayout + channels-last gather (round-1 path)
 
@@ -191,6 +192,18 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
                 return [grad_value, grad_loc, grad_attn]
             if rc != -3:
                 _C.check(rc, "mvd_msda_bwd_viewgrid_f32")
+    if _BWD_BANDED and value.dtype == torch.float32:  # encoder layout: same kernels, pairs walked band by band (L2-resident reds)
+        geo = _viewgrid_geometry(value, spatial_shapes, S, L, Lq)
+        if geo is not None:
+            H, W, R = geo
+            with _on_device(value):
+                rc = _C.lib.mvd_msda_bwd_banded_f32(grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(),
+                                                    level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                                                    attn_weight.data_ptr(), B, S, M, D, L, Lq, P, H, W, R,
+                                                    grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+                                                    _stream(value))
+            _C.check(rc, "mvd_msda_bwd_banded_f32")
+            return [grad_value, grad_loc, grad_attn]
     fn = _C.lib.mvd_msda_bwd_f32 if value.dtype == torch.float32 else _C.lib.mvd_msda_bwd_f64
     with _on_device(value):
         rc = fn(grad_output.data_ptr(), value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
@@ -680,7 +693,10 @@ def msda_bwd_kernel_name(value, hw, Lq):
     uniform = all(s == hw[0] for s in hw)
     if _BWD_VIEWGRID and uniform and value.dtype == torch.float32 and D in (8, 16, 32):
         return f"msda_vg_bwd_kernel<{D}> (TMA-staged view grid)"
-    return f"msda_bwd_vec4_kernel<{D}> (generic)" if D % 4 == 0 else "msda_bwd_scalar_kernel"
+    if D % 4 != 0:
+        return "msda_bwd_scalar_kernel"
+    banded = _BWD_BANDED and uniform and value.dtype == torch.float32 and Lq % (hw[0][0] * hw[0][1]) == 0
+    return f"msda_bwd_vec4_kernel<{D}> (" + ("pairs walked band by band" if banded else "generic, query order") + ")"
 
 
 def bias_act_(x, bias, relu=False):
