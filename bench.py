@@ -433,13 +433,14 @@ def ref_cuda_frame(fusion, ds, wl, device, ours_out, feat, proj, iters=10):
 
 def our_launches_per_frame(fusion, lt_gemm):
     """OUR kernels per frame: the warp (1 launch with the TMA kernel on the NCHW source, else relayout + gather); per
-    encoder layer 1 fused MSDA + 2 add_layernorm (the 2nd also emits the next layer's query) + the 6 Linear GEMMs when
+    encoder layer 1 fused MSDA + 2 add_layernorm (the 2nd also emits the next layer's query) + the 5 Linear GEMMs (offsets
+    and logits share one) when
     they run on our tcgen05 kernel (cuBLASLt launches are NOT counted; torch.mm mode adds 2 bias_act); on the GEMM conv
     path the downsample / merge / upsample-conv GEMMs (ours), upsample_im2col and the final NHWC->NCHW transpose."""
     from mvdetr_b200 import ops
     own = ops._GEMM_MODE in ("bf16x3", "f16x2", "tf32x3")
     n = ops.warp_launch_count(im2col=fusion.gemm_path)
-    n += LAYERS * (3 + (6 if own else 0) + (0 if (own or lt_gemm) else 2))
+    n += LAYERS * (3 + (5 if own else 0) + (0 if (own or lt_gemm) else 2))  # offsets + logits: one GEMM
     if fusion.gemm_path:
         n += 2 + (3 if own else 0)
     return n

@@ -137,6 +137,14 @@ MVD_API int mvd_msda_fused_fwd_viewgrid_f32(const float* value, const float* off
                                     const float* ref_lm, const float* off_bias, const float* logit_bias,
                                     int B, int H, int W, int M, int D, int L, int R, int P, int Lr,
                                     float* out, float* attn_out, float* loc_out, void* stream);
+/* Same call with offsets / logits given as COLUMN RANGES of wider rows: off_pitch / logit_pitch = floats between
+ * consecutive queries (multiples of 4, >= M*L*P*2 and M*L*P). Lets ONE GEMM over the concatenated weights of
+ * sampling_offsets and attention_weights (ref: ms_deform_attn.py:100-101) feed the kernel: the query rows are read and
+ * split once, one launch less per layer. */
+MVD_API int mvd_msda_fused_fwd_viewgrid_pitched_f32(const float* value, const float* offsets, const float* logits,
+                                            const float* ref, const float* off_bias, const float* logit_bias, int B,
+                                            int H, int W, int M, int D, int L, int R, int P, int Lr, int off_pitch,
+                                            int logit_pitch, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused sampling-location + softmax + deformable attention, forward ("next" row).

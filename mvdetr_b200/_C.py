@@ -31,6 +31,7 @@ SIGNATURES = {
     "mvd_msda_bwd_viewgrid_f32": [_p] * 4 + [_i] * 8 + [_p] * 4,
     "mvd_msda_fused_fwd_f32": [_p] * 8 + [_i] * 8 + [_p] * 4,
     "mvd_msda_fused_fwd_viewgrid_f32": [_p] * 6 + [_i] * 9 + [_p] * 4,
+    "mvd_msda_fused_fwd_viewgrid_pitched_f32": [_p] * 6 + [_i] * 11 + [_p, _p],
     "mvd_add_layernorm_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p],
     "mvd_add_layernorm_pos_f32": [_p] * 5 + [ctypes.c_int64, _i, ctypes.c_float, ctypes.c_int64, _p, _p, _p, _p],
     "mvd_warp_im2col_f32": [_p, _p] + [_i] * 7 + [_p, _p],

@@ -314,10 +314,16 @@ int launch_vg(const CUtensorMap* maps, const VgParams& prm, const VgPlan& pl, in
 template <bool FUSED>
 int viewgrid_dispatch(const float* value, const float* loc, const float* attn, const float* ref,
                       const float* off_bias, const float* logit_bias, int B, int H, int W, int M, int D, int L, int R,
-                      int P, int Lr, float* out, cudaStream_t st) {
+                      int P, int Lr, float* out, cudaStream_t st, int loc_pitch = 0, int attn_pitch = 0) {
+  // floats between consecutive queries in loc / attn: 0 = dense (M*L*P*2 and M*L*P); larger when both are column ranges
+  // of one [queries, M*L*P*3] GEMM output (offsets and logits produced by a single launch)
+  if (loc_pitch == 0) loc_pitch = M * L * P * 2;
+  if (attn_pitch == 0) attn_pitch = M * L * P;
+  if (loc_pitch < M * L * P * 2 || attn_pitch < M * L * P || (loc_pitch | attn_pitch) % 4 != 0) return MVD_ERR_BAD_SHAPE;
   if (B <= 0 || H <= 0 || W <= 0 || M <= 0 || D <= 0 || L <= 0 || R <= 0 || P <= 0) return MVD_ERR_BAD_SHAPE;
   // beyond the 32-bit indexing of this kernel: not an error, the generic kernel (64-bit indexing) takes the call
-  if ((int64_t)B * L * H * W * M * D > 0x7fffffffLL || (int64_t)B * R * H * W * M * L * P * 2 > 0x7fffffffffLL)
+  if ((int64_t)B * L * H * W * M * D > 0x7fffffffLL || (int64_t)B * R * H * W * M * L * P * 2 > 0x7fffffffffLL ||
+      (int64_t)B * R * H * W * (loc_pitch > attn_pitch ? loc_pitch : attn_pitch) > 0x7fffffffffLL)
     return MVD_ERR_UNSUPPORTED;
   if (M > 65535 || B > 65535) return MVD_ERR_UNSUPPORTED;
   if (!((D == 8 || D == 16 || D == 32) && (P == 4 || P == 8))) return MVD_ERR_UNSUPPORTED;
@@ -342,16 +348,16 @@ int viewgrid_dispatch(const float* value, const float* loc, const float* attn, c
     if (int e = encode(&maps[0], value, 5, gdim, gstr, box)) return e;
   }
   {  // loc / offsets [B*R][H][W][M][L*P*2]
-    const cuuint64_t n = u * L * P * 2;
+    const cuuint64_t n = u * L * P * 2, q = u * loc_pitch;
     const cuuint64_t gdim[5] = {n, u * M, u * W, u * H, u * B * R};
-    const cuuint64_t gstr[4] = {n * 4, n * M * 4, n * M * W * 4, n * M * W * H * 4};
+    const cuuint64_t gstr[4] = {n * 4, q * 4, q * W * 4, q * W * H * 4};
     const cuuint32_t box[5] = {(cuuint32_t)(2 * P), 1u, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, (cuuint32_t)R};
     if (int e = encode(&maps[1], loc, 5, gdim, gstr, box)) return e;
   }
   {  // attn / logits [B*R][H][W][M][L*P]
-    const cuuint64_t n = u * L * P;
+    const cuuint64_t n = u * L * P, q = u * attn_pitch;
     const cuuint64_t gdim[5] = {n, u * M, u * W, u * H, u * B * R};
-    const cuuint64_t gstr[4] = {n * 4, n * M * 4, n * M * W * 4, n * M * W * H * 4};
+    const cuuint64_t gstr[4] = {n * 4, q * 4, q * W * 4, q * W * H * 4};
     const cuuint32_t box[5] = {(cuuint32_t)P, 1u, (cuuint32_t)pl.TW, (cuuint32_t)pl.TH, (cuuint32_t)R};
     if (int e = encode(&maps[2], attn, 5, gdim, gstr, box)) return e;
   }
@@ -410,6 +416,18 @@ extern "C" int mvd_msda_fwd_viewgrid_f32(const float* value, const float* loc, c
                                          int W, int M, int D, int L, int R, int P, float* out, void* stream) {
   if (!value || !loc || !attn || !out) return MVD_ERR_NULL_POINTER;
   return viewgrid_dispatch<false>(value, loc, attn, nullptr, nullptr, nullptr, B, H, W, M, D, L, R, P, 1, out, (cudaStream_t)stream);
+}
+
+// offsets / logits as column ranges of wider rows (one GEMM producing both): pitches in floats per query, multiples of 4
+extern "C" int mvd_msda_fused_fwd_viewgrid_pitched_f32(const float* value, const float* offsets, const float* logits,
+                                                       const float* ref, const float* off_bias,
+                                                       const float* logit_bias, int B, int H, int W, int M, int D,
+                                                       int L, int R, int P, int Lr, int off_pitch, int logit_pitch,
+                                                       float* out, void* stream) {
+  if (!value || !offsets || !logits || !ref || !out) return MVD_ERR_NULL_POINTER;
+  if (Lr <= 0 || off_pitch <= 0 || logit_pitch <= 0) return MVD_ERR_BAD_SHAPE;
+  return viewgrid_dispatch<true>(value, offsets, logits, ref, off_bias, logit_bias, B, H, W, M, D, L, R, P, Lr, out,
+                                 (cudaStream_t)stream, off_pitch, logit_pitch);
 }
 
 extern "C" int mvd_msda_fused_fwd_viewgrid_f32(const float* value, const float* offsets, const float* logits,

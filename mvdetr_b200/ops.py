@@ -264,12 +264,30 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
     and selects the TMA-staged view-grid kernel; the generic kernel is used when that layout has no instantiation.
     ref_table_lm: optional precomputed level-major copy of ref_table, [L,Lr,P,2] (made on the fly when None).
     off_bias [M*L*P*2] / logit_bias [M*L*P]: optional biases of the two Linear layers, added in the kernel so the
-    caller can run both as bias-free GEMMs (cuBLASLt applies an fp32 bias in a separate pass over the output)."""
+    caller can run both as bias-free GEMMs (cuBLASLt applies an fp32 bias in a separate pass over the output).
+    offsets / logits may also be the two column ranges of ONE contiguous [B*Lq, M*L*P*3] GEMM output (views with that row
+    pitch): the view-grid kernel reads them in place through strided tensor maps."""
     B, S, M, D = value.shape
     _, Lq, _, L, P, _ = offsets.shape
-    for name, t in (("value", value), ("offsets", offsets), ("logits", logits), ("ref_table", ref_table)):
+    for name, t in (("value", value), ("ref_table", ref_table)):
         if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
             raise RuntimeError(f"{name} must be a contiguous fp32 CUDA tensor")
+    off_pitch, log_pitch = M * L * P * 2, M * L * P
+    pitched = False
+    if not (offsets.is_contiguous() and logits.is_contiguous()):
+        # accepted: rows [B*Lq] with a common pitch, dense inside a row
+        o2, l2 = offsets.reshape(B * Lq, off_pitch) if offsets.dim() == 6 else offsets, logits.reshape(B * Lq, log_pitch)
+        if not (o2.stride(1) == 1 and l2.stride(1) == 1 and o2.stride(0) == l2.stride(0) and o2.stride(0) % 4 == 0 and
+                o2.data_ptr() % 16 == 0 and l2.data_ptr() % 16 == 0 and o2.data_ptr() == offsets.data_ptr()):
+            raise RuntimeError("msda_fused_forward: offsets / logits must be contiguous or column ranges of one row-major buffer")
+        off_pitch = log_pitch = o2.stride(0)
+        pitched = True
+        if want_aux or grid_hw is None or not _VIEWGRID:  # only the view-grid kernel reads strided rows
+            offsets, logits, pitched = offsets.contiguous(), logits.contiguous(), False
+            off_pitch, log_pitch = M * L * P * 2, M * L * P
+    for name, t in (("offsets", offsets), ("logits", logits)):
+        if not (t.is_cuda and t.dtype == torch.float32):
+            raise RuntimeError(f"{name} must be a fp32 CUDA tensor")
     if logits.numel() != B * Lq * M * L * P or tuple(ref_table.shape[1:]) != (L, P, 2):
         raise RuntimeError("msda_fused_forward: inconsistent shapes")
     for name, t, n in (("off_bias", off_bias, M * L * P * 2), ("logit_bias", logit_bias, M * L * P)):
@@ -290,15 +308,23 @@ def msda_fused_forward(value, spatial_shapes, level_start_index, offsets, logits
                 ref_table_lm = ref_table.permute(1, 0, 2, 3).contiguous()
             elif tuple(ref_table_lm.shape) != (L, ref_table.shape[0], P, 2) or not ref_table_lm.is_contiguous():
                 raise RuntimeError("msda_fused_forward: ref_table_lm must be contiguous [L, Lr, P, 2]")
-            rc = _C.lib.mvd_msda_fused_fwd_viewgrid_f32(value.data_ptr(), offsets.data_ptr(), logits.data_ptr(),
-                                                        ref_table_lm.data_ptr(), ob, lb, B, H, W, M, D, L,
-                                                        Lq // (H * W), P,
-                                                        ref_table.shape[0], out.data_ptr(), None, None,
-                                                        _stream(value))
+            if pitched:
+                rc = _C.lib.mvd_msda_fused_fwd_viewgrid_pitched_f32(value.data_ptr(), offsets.data_ptr(),
+                                                                    logits.data_ptr(), ref_table_lm.data_ptr(), ob, lb, B,
+                                                                    H, W, M, D, L, Lq // (H * W), P, ref_table.shape[0],
+                                                                    off_pitch, log_pitch, out.data_ptr(), _stream(value))
+            else:
+                rc = _C.lib.mvd_msda_fused_fwd_viewgrid_f32(value.data_ptr(), offsets.data_ptr(), logits.data_ptr(),
+                                                            ref_table_lm.data_ptr(), ob, lb, B, H, W, M, D, L,
+                                                            Lq // (H * W), P,
+                                                            ref_table.shape[0], out.data_ptr(), None, None,
+                                                            _stream(value))
             if rc == 0:
                 return (out, attn, loc) if want_aux else out
             if rc != -3:  # MVD_ERR_UNSUPPORTED -> generic kernel
                 _C.check(rc, "mvd_msda_fused_fwd_viewgrid_f32")
+        if pitched:  # the generic kernel reads dense tensors
+            offsets, logits = offsets.contiguous(), logits.contiguous()
         rc = _C.lib.mvd_msda_fused_fwd_f32(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                                            offsets.data_ptr(), logits.data_ptr(), ref_table.data_ptr(), ob, lb, B, S,
                                            M, D, L, Lq, P, ref_table.shape[0], out.data_ptr(), *aux, _stream(value))

@@ -228,8 +228,7 @@ class ShardedFusion:
             if nq:
                 query = next_query if next_query is not None else src + pos
                 # bias-free GEMMs; the biases are applied inside our kernels (world_feat.MSDeformAttn.forward)
-                offsets = ops.linear(query, attn.sampling_offsets.weight).view(1, nq, M, L, P, 2)
-                logits = ops.linear(query, attn.attention_weights.weight).view(1, nq, M, L * P)
+                offsets, logits = attn.offsets_and_logits(query, 1, nq)   # one GEMM, column ranges of its output
             if cur is not None:
                 cur.wait_event(join)
             if nq:

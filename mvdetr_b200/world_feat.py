@@ -106,6 +106,24 @@ class MSDeformAttn(nn.Module):
                 xavier_uniform_(proj.weight)
                 proj.bias.zero_()
 
+    def offsets_and_logits(self, q2, N, Len_q, packed=True):
+        """Raw (bias-free) outputs of sampling_offsets and attention_weights for the query rows q2 [N*Len_q, C]:
+        -> ([N,Len_q,M,L,P,2], [N,Len_q,M,L*P]). packed: ONE GEMM over the concatenated weights (the query rows are read
+        and split once, one launch less); the two results are column ranges of its output, which the view-grid MSDA
+        kernel reads in place. ref: ms_deform_attn.py:100-101."""
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        no, nl = M * L * P * 2, M * L * P
+        if not packed:
+            return (ops.linear(q2, self.sampling_offsets.weight).view(N, Len_q, M, L, P, 2),
+                    ops.linear(q2, self.attention_weights.weight).view(N, Len_q, M, L * P))
+        ws = (self.sampling_offsets.weight, self.attention_weights.weight)
+        key = getattr(self, "_ol_key", None)
+        if not (key is not None and all(r() is w and v == w._version for (r, v), w in zip(key, ws))):
+            self._ol_w = torch.cat([w.detach() for w in ws], 0).contiguous()   # [M*L*P*3, C]
+            self._ol_key = [(weakref.ref(w), w._version) for w in ws]
+        both = ops.linear(q2, self._ol_w)                                       # [N*Len_q, M*L*P*3]
+        return both[:, :no].view(N, Len_q, M, L, P, 2), both[:, no:].view(N, Len_q, M, L * P)
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None, geometry=None, ref_table=None, ref_table_lm=None, defer_output_bias=False):
         """Reference signature (first six arguments). Extensions used by our encoder: `geometry` (LevelGeometry,
@@ -136,9 +154,8 @@ class MSDeformAttn(nn.Module):
             # both Linear layers as bias-free GEMMs (ops.linear: tensor-core fp32 emulation when the toolkit's cuBLASLt
             # is available); the biases are added inside the MSDA kernel before the same arithmetic as the reference
             q2 = query.reshape(N * Len_q, -1)
-            sampling_offsets = ops.linear(q2, self.sampling_offsets.weight).view(N, Len_q, M, L, P, 2)
-            attention_weights = ops.linear(q2, self.attention_weights.weight).view(N, Len_q, M, L * P)
             grid_hw = geometry.hw[0] if geometry is not None and geometry.uniform else None
+            sampling_offsets, attention_weights = self.offsets_and_logits(q2, N, Len_q, packed=grid_hw is not None)
             output = ops.msda_fused_forward(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                             sampling_offsets, attention_weights, ref_table,
                                             grid_hw=grid_hw, ref_table_lm=ref_table_lm,

@@ -273,6 +273,16 @@ def test_viewgrid_fused_matches_unfused_and_generic(cuda):
     sub = ops.msda_fused_forward(value, shapes, start, offsets[:, 2 * hw:5 * hw].contiguous(),
                                  logits[:, 2 * hw:5 * hw].contiguous(), table, grid_hw=(H, W))
     assert torch.equal(sub, o_vg[:, 2 * hw:5 * hw])
+    # offsets / logits as column ranges of one [Lq, M*L*P*3] buffer (one GEMM for both Linear layers): read in place
+    no, nl = M * L * P * 2, M * L * P
+    both = torch.cat((offsets.view(Lq, no), logits.view(Lq, nl)), 1).contiguous()
+    packed = ops.msda_fused_forward(value, shapes, start, both[:, :no].view(1, Lq, M, L, P, 2),
+                                    both[:, no:].view(1, Lq, M, L * P), table, grid_hw=(H, W))
+    assert torch.equal(packed, o_vg)
+    # ... and through the generic kernel (no grid): densified copies, same results as the dense call
+    packed_gen = ops.msda_fused_forward(value, shapes, start, both[:, :no].view(1, Lq, M, L, P, 2),
+                                        both[:, no:].view(1, Lq, M, L * P), table)
+    assert torch.equal(packed_gen, o_gen)
 
 
 @pytest.mark.parametrize("grid", [True, False])
