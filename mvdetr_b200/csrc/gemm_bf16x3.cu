@@ -1,29 +1,37 @@
 // Dense glue of the path on the 5th-generation tensor cores with fp32-level accuracy, as ONE persistent kernel per layer:
 //   out[rows, N] = act(x[rows, K] @ W[N, K]^T + bias[N])
-//   replaces the six nn.Linear calls per encoder layer  ref: multiview_detector/models/ops/modules/ms_deform_attn.py:96,100-101,116,
+//   replaces the nn.Linear calls of an encoder layer    ref: multiview_detector/models/ops/modules/ms_deform_attn.py:96,100-101,116,
 //                                                        multiview_detector/models/deformable_transformer.py:82
-//   and, through the im2col matrices written by warp_tma.cu / im2col.cu, the convolutions of
-//                                                        ref: multiview_detector/models/trans_world_feat.py:74,82-84
+//   and the 3x3 convolutions (implicit GEMM: taps fetched by TMA from the channels-last map, or a materialised im2col
+//   matrix) and the 1x1 merge                            ref: multiview_detector/models/trans_world_feat.py:74,82-84,107-109
 //
 // Why ours: round 1 used cuBLASLt's CUBLAS_COMPUTE_32F_EMULATED_16BFX9 -- 9 bf16 products, a bias pass and a separate
 // Inf/NaN operand-scan kernel per call (profiles/r02c_timeline.txt: GEMM 1.34 ms + scan/patch 0.8 ms of a 3.2 ms frame).
-// The layers are tall-skinny (75 600 x 128 by 128 x {128..512}; ~10 flop/byte): HBM-bound, so the job is to stream x once.
+// The layers are tall-skinny (75 600 x 128..1152 by 128..672; ~10 flop/byte).
 //
-// Arithmetic: fp32 operands are split into three bf16 terms (a = a0 + a1 + a2, each the bf16 rounding of the remaining
-// residual; 24 mantissa bits covered) and the SIX products with i + j <= 2 are accumulated in fp32 in tensor memory
-// (scripts/emulate_bf16_split.py: the dropped three are below 2^-24 |a||b|; measured error vs fp64 at cuBLASLt BF16x9's
-// level, below a native fp32 GEMM). bf16 products are exact inside the tensor core's adder (16-bit significands), which
-// a 3xTF32 split is not (22-bit products: csrc/gemm_tf32.cu measures 5-10x larger error).
+// Two kernels in this file:
+//  * linear_split_ts_kernel<NT> (DEFAULT, second half of the file): x terms staged in TENSOR MEMORY, NT = 2 fp16 terms /
+//    3 products (default) or NT = 3 bf16 terms / 6 products; own producer warps for x and W, converged issue warps
+//    under elect.sync, conv mode, optional NVLink-multicast epilogue. Its header comment has the structure.
+//  * linear_bf16x3_kernel (below; MVDETR_B200_GEMM=bf16x3 with MVDETR_B200_GEMM_TS=0, mode "bf16x3ss"): the round-2
+//    first version with both operands in shared memory, kept as the bit-identical comparator of the NT = 3 variant.
 //
-// Structure (1 CTA per SM, persistent over 128 x 128 output tiles, 320 threads, 3-stage ring, warp-specialised):
+// Arithmetic of the bf16 variants: fp32 operands are split into three bf16 terms (a = a0 + a1 + a2, each the bf16 rounding
+// of the remaining residual; 24 mantissa bits covered) and the SIX products with i + j <= 2 are accumulated in fp32 in
+// tensor memory (scripts/emulate_bf16_split.py: the dropped three are below 2^-24 |a||b|). bf16 products are exact inside
+// the tensor core's adder (16-bit significands), which a 3xTF32 split is not (22-bit products: csrc/gemm_tf32.cu measures
+// 5-10x larger error).
+//
+// Structure of linear_bf16x3_kernel (1 CTA per SM, persistent over 128 x 128 output tiles, 320 threads, warp-specialised):
 //   warp 0      TMA producer: per 32-wide K chunk the x tile [128 x 32] fp32 (SWIZZLE_128B) and the three pre-split
 //               weight tiles [128 x 32] bf16 (SWIZZLE_64B; rows past `rows` / `N`, columns past K are zero-filled);
 //   warps 2-5   split the x tile into three bf16 tiles in the UMMA K-major SWIZZLE_64B layout (thread = row: conflict-
 //               free 16-byte reads of the 128B-swizzled source and 16-byte writes of the 64B-swizzled destinations);
-//   warp 1      one thread issues 2 k-steps x 6 tcgen05.mma.kind::f16 (M 128, N 128, K 16) per chunk, commits the stage
-//               back to the producer, and after the last chunk commits the accumulator to the epilogue;
-//   warps 6-9   epilogue: tcgen05.ld 32 lanes x 16 columns of both accumulators, sum + bias, ReLU, 16-byte stores of
-//               their own rows, overlapping the next tile's main loop (2 x 2 x 128 accumulator columns in tensor memory).
+//   warp 1      converged; an elected lane issues 2 k-steps x 6 tcgen05.mma.kind::f16 (M 128, N 128, K 16) per chunk,
+//               commits the stages back to their producers, and after the last chunk the accumulator to the epilogue;
+//   warps 6-9   epilogue: tcgen05.ld of both accumulators, sum + bias, ReLU, 32 x 32 sub-tiles transposed through shared
+//               memory into full 128-byte row segments, overlapping the next tile's main loop (2 x 2 x 128 accumulator
+//               columns in tensor memory).
 #include <cuda.h>
 
 #include <cstdio>
@@ -371,12 +379,14 @@ __global__ void __launch_bounds__(kBThreads, 1)
 // moves 176 KB through shared memory (TMA fill 40, split read 16 + write 24, UMMA operand reads 48 (x) + 48 (W)), 0.87 us
 // measured against 0.40 us of tensor time. Here the splitters write their three bf16 terms with tcgen05.st into tensor
 // memory (lane = row, one 32-bit column = two consecutive k) and the MMAs take A from there ("TS" form of tcgen05.mma):
-// 104 KB per chunk. When K <= 128 the whole row block of x stays in tensor memory (4 stages x 48 columns) and is reused by
-// every 128-column tile of the output (N = 224 / 448 / 512 layers: x is read from HBM and split ONCE per row block).
-//   tensor memory: columns 0-127 leading-product accumulator, 128-255 small-terms accumulator, 256-447 x-term stages
+// 104 KB per chunk (72 KB with two terms). When the K chunks of a row block fit the term stages (NT = 2: K <= 256, 8 stages
+// x 32 columns; NT = 3: K <= 160) the terms stay in tensor memory and are reused by every 128-column tile of the output
+// (N = 512 / 672 layers: x is read from HBM and split ONCE per row block).
+//   tensor memory: columns 0-127 leading-product accumulator, 128-255 small-terms accumulator, 256-511 x-term stages
 //   (one accumulator buffer: the 8 epilogue warps first drain it into registers and hand it back, then do bias / ReLU /
 //   stores under the next tile's main loop)
-//   warps: 0 TMA, 1 MMA, 2-5 split (TMEM lane quarter = warp & 3), 6-13 epilogue (quarter = warp & 3, column half)
+//   warps: 0 x-tile TMA, 1 MMA, 2-5 split (TMEM lane quarter = warp & 3), 6-13 epilogue (quarter = warp & 3, column
+//   half), 14 weight-term TMA
 constexpr int kTsThreads = 480;  // warps: 0 x-tile TMA, 1 MMA, 2-5 split, 6-13 epilogue, 14 weight-term TMA
 constexpr uint32_t kTsAccCols = 2 * kBN;      // leading + small-terms accumulators
 constexpr uint32_t kTsTmemCols = 512;
