@@ -95,3 +95,37 @@ def test_every_binding_call_passes_the_declared_number_of_arguments():
                     assert len(node.args) == want, (f, node.lineno, node.func.attr)
                 seen += 1
     assert seen >= 15
+
+
+def test_hot_kernels_are_sm100a_native_in_sass():
+    """SASS of the built library (no GPU needed): the hot-path kernels stage through TMA (UTMALDG) and mbarriers (SYNCS),
+    the GEMM issues tcgen05 MMAs with the A operand in tensor memory (UTCHMMA tmem[..], gdesc[..]) fed by tcgen05.st
+    (STTM), and none of them carries the uniform-register waterfall (BRA.U.ANY) that a divergent issue loop gets."""
+    import shutil
+    from mvdetr_b200 import _C
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", _C.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    per_kernel, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_kernel[name] = []
+        elif name is not None:
+            per_kernel[name].append(line)
+
+    def kernels(tag):
+        ks = {k: "\n".join(v) for k, v in per_kernel.items() if tag in k}
+        assert ks, f"no kernel named *{tag}* in the library"
+        return ks
+
+    for tag in ("linear_split_ts_kernel", "warp_tma_cl_kernel", "msda_vg_kernel"):
+        for k, text in kernels(tag).items():
+            assert "UTMALDG" in text and "SYNCS" in text, k
+            assert "BRA.U.ANY" not in text, f"{k}: issue loop fell back to a uniform-register waterfall"
+    for k, text in kernels("linear_split_ts_kernel").items():
+        assert re.search(r"UTCHMMA tmem\[\w+\], gdesc\[\w+\], tmem\[", text), f"{k}: MMA does not take A from tensor memory"
+        assert "STTM" in text and "LDTM" in text and "UTCBAR" in text, k
