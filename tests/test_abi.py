@@ -129,3 +129,11 @@ def test_hot_kernels_are_sm100a_native_in_sass():
     for k, text in kernels("linear_split_ts_kernel").items():
         assert re.search(r"UTCHMMA tmem\[\w+\], gdesc\[\w+\], tmem\[", text), f"{k}: MMA does not take A from tensor memory"
         assert "STTM" in text and "LDTM" in text and "UTCBAR" in text, k
+
+
+def test_every_export_is_mapped_to_a_reference_interface_in_the_docs():
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    missing = [n for n in declared_functions() if n not in doc]
+    assert not missing, f"INTEGRATION.md does not mention {missing}"
+    header = open(HEADER).read()
+    assert header.count("ref:") + header.count("ref ") >= 10   # entry points cite the reference interface they replace
