@@ -5,6 +5,6 @@ TAG="${1:-r02ab}"
 mkdir -p gpurun_out
 : > gpurun_out/${TAG}_frame_error.jsonl
 for MODE in f16x2 bf16x3; do
-  MVDETR_B200_GEMM=$MODE timeout -s KILL 400 python scripts/frame_error.py >> gpurun_out/${TAG}_frame_error.jsonl 2>> gpurun_out/${TAG}_frame_error.err
+  MVDETR_B200_GEMM=$MODE timeout -s KILL 400 python tests/frame_error.py >> gpurun_out/${TAG}_frame_error.jsonl 2>> gpurun_out/${TAG}_frame_error.err
 done
 cat gpurun_out/${TAG}_frame_error.jsonl; tail -3 gpurun_out/${TAG}_frame_error.err

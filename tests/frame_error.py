@@ -1,4 +1,4 @@
-"""Error budget of the full-size frame: ours (GPU, fp32-level GEMMs) vs the CPU oracle in fp32 and in fp64, and the fp32
+"""Test-side tool (uses the oracle, so it lives under tests/). Error budget of the full-size frame: ours (GPU, fp32-level GEMMs) vs the CPU oracle in fp32 and in fp64, and the fp32
 oracle vs the fp64 oracle (how much of the 1e-4 parity bar the fp32 REFERENCE arithmetic itself consumes)."""
 import json
 import os
@@ -10,7 +10,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from mvdetr_b200 import ops, synthetic  # noqa: E402
 from mvdetr_b200.fusion import FrameRunner, MultiviewFusion  # noqa: E402
-from oracle import c_oracle as co  # noqa: E402
+from oracle import cpu_oracle as co  # noqa: E402
 from oracle import torch_port as tp  # noqa: E402
 
 
